@@ -1,0 +1,429 @@
+// bgx_cuda.cu -- CUDA kernels + C ABI (include/brotlig_b200.h) of the B200-native Brotli-G decompressor.
+//
+// Replaces, for the decode path only:
+//   src/decoder/BrotliGCompute.hlsl (CSMain :1753-1881: persistent waves pulling pages with atomics)
+//       -> bgx_decode_pages_kernel: persistent one-warp CTAs, one atomic page counter over ALL streams
+//   sample/BrotligGPUDecoder.cpp (DecodeGPU :260-748: upload, Dispatch, readback, timestamp queries)
+//       -> bgx_decode_host / bgx_decode_batch_host / bgx_plan_*: CUDA stream + events
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a (see brotli_g_sdk_b200/build.py).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/brotlig_b200.h"
+#include "bgx_format.h"
+#include "host_plan.h"
+#include "page_decode.cuh"
+
+namespace {
+
+using bgx::PreconLayout;
+using bgx::StreamInfo;
+
+// ------------------------------------------------------------------------------------ device side
+struct StreamDev {
+  const uint8_t* table;     // page table (device)
+  const uint8_t* pages;     // first page byte
+  const uint8_t* src_end;   // one past the last readable byte of the stream buffer
+  uint8_t* dst;             // where page `page_begin` goes (texture streams: the conditioned scratch planes)
+  uint32_t num_pages, page_size, last_page_size;
+  uint32_t page_begin;      // first page of the stream this plan decodes
+  uint32_t first_q;         // position of that page in the flat work queue
+  uint32_t allow_delta;
+  bgxk::DeltaPlanes planes; // colour planes for the per-page delta decode
+};
+
+struct QueueCtl {
+  uint32_t next_page;       // atomic work counter (cf. meta.InterlockedAdd, BrotliGCompute.hlsl:1815)
+  uint32_t bad_pages;       // pages whose decode reported an error
+};
+
+__global__ void __launch_bounds__(32) bgx_decode_pages_kernel(const StreamDev* __restrict__ streams, uint32_t nstreams,
+                                                              uint32_t total_pages, QueueCtl* ctl,
+                                                              uint32_t* __restrict__ page_status) {
+  __shared__ bgxk::WarpSmem sm;
+  const uint32_t lane = threadIdx.x;
+  for (;;) {
+    uint32_t q = 0;
+    if (lane == 0) q = atomicAdd(&ctl->next_page, 1u);
+    q = __shfl_sync(bgxk::kFull, q, 0);
+    if (q >= total_pages) break;
+    // stream owning queue slot q: last stream with first_q <= q
+    uint32_t lo = 0, hi = nstreams;
+    while (hi - lo > 1) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (streams[mid].first_q <= q) lo = mid; else hi = mid;
+    }
+    const StreamDev& s = streams[lo];
+    const uint32_t page = s.page_begin + (q - s.first_q);
+    StreamInfo si;
+    si.num_pages = s.num_pages;
+    si.page_size = s.page_size;
+    si.last_page_size = s.last_page_size;
+    const bgx::PageExtent e = bgx::page_extent(si, s.table, page);
+    const uint8_t* in = s.pages + e.in_off;
+    uint8_t* out = s.dst + (size_t)(page - s.page_begin) * s.page_size;
+    uint32_t status = 0;
+    if (e.in_size == e.out_size) {
+      bgxk::copy_page_warp(out, in, e.out_size);
+    } else {
+      bgxk::PageJob job;
+      job.in = in;
+      job.in_size = e.in_size;
+      const size_t room = (size_t)(s.src_end - in);
+      job.in_limit = room > 0xfffffff0u ? 0xfffffff0u : (uint32_t)room;
+      job.out = out;
+      job.out_size = e.out_size;
+      job.allow_delta = s.allow_delta;
+      if (e.in_size < 8u || in + e.in_size > s.src_end) {
+        status = bgxk::kPageErrTable;
+      } else {
+        const bgxk::PageResult r = bgxk::decode_page_warp(job, &sm);
+        status = r.status;
+        if (!status && r.is_delta) {
+          __syncwarp();
+          bgxk::delta_decode_warp(out, e.out_off, e.out_size, s.planes);
+          status |= 0x40000000u;   // informational: page was delta coded
+        }
+      }
+    }
+    if (lane == 0) {
+      page_status[q] = status;
+      if (status & 0xffffu) atomicAdd(&ctl->bad_pages, 1u);
+    }
+    __syncwarp();
+  }
+}
+
+// one thread per texture block: gather the block's fields from the planes, write the block
+__global__ void __launch_bounds__(256) bgx_decondition_kernel(const PreconLayout* __restrict__ layout,
+                                                              const uint8_t* __restrict__ planes, uint8_t* tex) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < layout->total_blocks) bgxk::decondition_block(*layout, t, planes, tex);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------ host side
+struct bgx_context {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int sm_count = 0;
+  int blocks_per_sm = 0;
+  std::string err;
+  // grow-only device arenas for the host-pointer entry points
+  uint8_t* d_in = nullptr;
+  size_t d_in_cap = 0;
+  uint8_t* d_out = nullptr;
+  size_t d_out_cap = 0;
+};
+
+struct PreconJob {
+  PreconLayout layout;
+  PreconLayout* d_layout = nullptr;
+  uint8_t* d_planes = nullptr;    // conditioned scratch (decode target)
+  uint8_t* d_tex = nullptr;       // final output
+  uint32_t out_size = 0;
+  bool has_padding = false;
+};
+
+struct bgx_plan {
+  std::vector<StreamDev> h_streams;
+  StreamDev* d_streams = nullptr;
+  QueueCtl* d_ctl = nullptr;
+  uint32_t* d_status = nullptr;
+  uint32_t total_pages = 0;
+  std::vector<PreconJob> precon;
+  uint8_t* d_scratch = nullptr;   // backing store of all conditioned scratch planes
+  bgx_plan_info info{};
+  cudaStream_t last_stream = nullptr;
+};
+
+namespace {
+
+int fail(bgx_context* ctx, const char* what, cudaError_t e) {
+  if (ctx) ctx->err = std::string(what) + ": " + cudaGetErrorString(e);
+  return bgx::kErrGeneric;
+}
+#define BGX_CUDA(ctx, call)                                  \
+  do {                                                       \
+    cudaError_t e_ = (call);                                 \
+    if (e_ != cudaSuccess) return fail(ctx, #call, e_);      \
+  } while (0)
+
+int grow(bgx_context* ctx, uint8_t** p, size_t* cap, size_t need) {
+  if (need <= *cap) return 0;
+  if (*p) BGX_CUDA(ctx, cudaFree(*p));
+  *p = nullptr;
+  *cap = 0;
+  const size_t want = need + need / 8 + 4096;
+  BGX_CUDA(ctx, cudaMalloc(p, want));
+  *cap = want;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+uint32_t bgx_decompressed_size(const uint8_t* src) {
+  StreamInfo si;
+  // DecompressedSize does not validate (BrotligDecoder.cpp:34-38); neither do we.
+  const uint32_t w0 = bgx::load_le32(src), w1 = bgx::load_le32(src + 4);
+  si.num_pages = w0 >> 16;
+  si.page_size = bgx::kMinPageSize << (w1 & 3u);
+  si.last_page_size = (w1 >> 2) & 0x3ffffu;
+  return si.num_pages * si.page_size - (si.last_page_size ? si.page_size - si.last_page_size : 0u);
+}
+
+int bgx_create(bgx_context** out, int device) {
+  *out = nullptr;
+  bgx_context* ctx = new bgx_context();
+  cudaError_t e;
+  if (device < 0) {
+    e = cudaGetDevice(&device);
+    if (e != cudaSuccess) { fprintf(stderr, "brotlig_b200: no CUDA device: %s\n", cudaGetErrorString(e)); delete ctx; return bgx::kErrGeneric; }
+  }
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess) { fprintf(stderr, "brotlig_b200: cudaSetDevice(%d): %s\n", device, cudaGetErrorString(e)); delete ctx; return bgx::kErrGeneric; }
+  ctx->device = device;
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) { fprintf(stderr, "brotlig_b200: cudaGetDeviceProperties: %s\n", cudaGetErrorString(e)); delete ctx; return bgx::kErrGeneric; }
+  ctx->sm_count = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
+    fprintf(stderr, "brotlig_b200: stream/event creation failed\n");
+    delete ctx;
+    return bgx::kErrGeneric;
+  }
+  // one-warp CTAs, as many as the shared-memory arena allows per SM
+  cudaFuncSetAttribute(bgx_decode_pages_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  int per_sm = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bgx_decode_pages_kernel, 32, 0);
+  if (e != cudaSuccess || per_sm < 1) {
+    fprintf(stderr, "brotlig_b200: kernel image not usable on this device (%s); built for sm_100a\n", cudaGetErrorString(e));
+    delete ctx;
+    return bgx::kErrGeneric;
+  }
+  ctx->blocks_per_sm = per_sm;
+  *out = ctx;
+  return bgx::kOk;
+}
+
+void bgx_destroy(bgx_context* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->d_in) cudaFree(ctx->d_in);
+  if (ctx->d_out) cudaFree(ctx->d_out);
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* bgx_last_error(const bgx_context* ctx) { return ctx ? ctx->err.c_str() : "no context"; }
+
+void bgx_plan_destroy(bgx_plan* plan) {
+  if (!plan) return;
+  if (plan->d_streams) cudaFree(plan->d_streams);
+  if (plan->d_ctl) cudaFree(plan->d_ctl);
+  if (plan->d_status) cudaFree(plan->d_status);
+  if (plan->d_scratch) cudaFree(plan->d_scratch);
+  for (auto& p : plan->precon)
+    if (p.d_layout) cudaFree(p.d_layout);
+  delete plan;
+}
+
+void bgx_plan_get_info(const bgx_plan* plan, bgx_plan_info* info) { *info = plan->info; }
+
+int bgx_plan_create(bgx_context* ctx, const bgx_stream* streams, uint32_t n, bgx_plan** out) {
+  *out = nullptr;
+  BGX_CUDA(ctx, cudaSetDevice(ctx->device));
+  bgx_plan* plan = new bgx_plan();
+  struct Guard { bgx_plan* p; ~Guard() { if (p) bgx_plan_destroy(p); } } guard{plan};
+  uint64_t scratch_bytes = 0;
+  std::vector<size_t> scratch_off;
+  for (uint32_t i = 0; i < n; ++i) {
+    const bgx_stream& s = streams[i];
+    StreamInfo si;
+    const int rc = bgx::parse_stream_header(s.header, &si);
+    if (rc) { ctx->err = "stream " + std::to_string(i) + ": bad header"; return rc; }
+    if ((reinterpret_cast<uintptr_t>(s.d_src) & 3u) != 0) { ctx->err = "stream pointer must be 4-byte aligned"; return bgx::kErrGeneric; }
+    const uint64_t table_end = (uint64_t)si.header_bytes + 4ull * si.num_pages;
+    if (table_end > s.src_size || s.src_capacity < s.src_size) { ctx->err = "stream " + std::to_string(i) + ": truncated"; return bgx::kErrCorruptStream; }
+    uint32_t begin = s.page_begin, count = s.page_count ? s.page_count : (si.num_pages > begin ? si.num_pages - begin : 0);
+    if (begin > si.num_pages || count > si.num_pages - begin) { ctx->err = "page range outside the stream"; return bgx::kErrGeneric; }
+    if (count == 0) continue;
+    const bool whole = begin == 0 && count == si.num_pages;
+    // bytes this range produces
+    uint64_t produced = (uint64_t)count * si.page_size;
+    if (begin + count == si.num_pages && si.last_page_size) produced -= si.page_size - si.last_page_size;
+    if (produced > s.dst_capacity) { ctx->err = "stream " + std::to_string(i) + ": output buffer too small"; return bgx::kErrGeneric; }
+
+    StreamDev d{};
+    d.table = s.d_src + si.header_bytes;
+    d.pages = d.table + 4ull * si.num_pages;
+    d.src_end = s.d_src + s.src_capacity;
+    d.dst = s.d_dst;
+    d.num_pages = si.num_pages;
+    d.page_size = si.page_size;
+    d.last_page_size = si.last_page_size;
+    d.page_begin = begin;
+    d.first_q = plan->total_pages;
+    d.allow_delta = si.preconditioned;
+    if (si.preconditioned) {
+      if (!whole) { ctx->err = "page ranges of pre-conditioned streams are not supported"; return bgx::kErrGeneric; }
+      const bgx::PreconHeaderFields f = bgx::parse_precon_header(s.header + 8);
+      PreconJob pj;
+      // BrotligDecoder.cpp:478 sizes the layout from the caller's buffer size; we require the exact size
+      if (!bgx::precon_layout_init(&pj.layout, f.format, f.width_blocks, f.height_blocks, f.pitch_bytes, f.num_mips,
+                                   f.swizzled != 0, f.pitch_aligned != 0, si.uncompressed_size)) {
+        ctx->err = "stream " + std::to_string(i) + ": texture layout does not match the stream size";
+        return bgx::kErrCorruptStream;
+      }
+      pj.d_tex = s.d_dst;
+      pj.out_size = si.uncompressed_size;
+      pj.has_padding = (uint64_t)pj.layout.total_blocks * pj.layout.block_bytes != si.uncompressed_size;
+      d.planes.count = pj.layout.num_color_sub;
+      for (uint32_t c = 0; c < pj.layout.num_color_sub; ++c) {
+        d.planes.lo[c] = pj.layout.sub_stream_off[pj.layout.color_sub[c]];
+        d.planes.hi[c] = pj.layout.sub_stream_off[pj.layout.color_sub[c] + 1];
+      }
+      scratch_off.push_back((size_t)scratch_bytes);
+      scratch_bytes += ((uint64_t)si.uncompressed_size + 255u) & ~255ull;
+      plan->precon.push_back(pj);
+      d.dst = nullptr;   // patched below once the scratch arena exists
+      d.allow_delta = 1u | ((uint32_t)plan->precon.size() << 8);   // remember which precon job (index+1) in the high bits
+    }
+    plan->h_streams.push_back(d);
+    plan->total_pages += count;
+    plan->info.compressed_bytes += s.src_size;   // whole-stream bytes; page ranges read a subset (reported as upper bound)
+    plan->info.uncompressed_bytes += produced;
+  }
+  plan->info.pages = plan->total_pages;
+  if (scratch_bytes) {
+    BGX_CUDA(ctx, cudaMalloc(&plan->d_scratch, scratch_bytes));
+    for (auto& d : plan->h_streams) {
+      if (d.allow_delta >> 8) {
+        const size_t k = (d.allow_delta >> 8) - 1;
+        plan->precon[k].d_planes = plan->d_scratch + scratch_off[k];
+        d.dst = plan->precon[k].d_planes;
+        d.allow_delta = 1;
+      }
+    }
+    for (auto& p : plan->precon) {
+      BGX_CUDA(ctx, cudaMalloc(&p.d_layout, sizeof(PreconLayout)));
+      BGX_CUDA(ctx, cudaMemcpy(p.d_layout, &p.layout, sizeof(PreconLayout), cudaMemcpyHostToDevice));
+    }
+  }
+  const size_t ns = std::max<size_t>(plan->h_streams.size(), 1);
+  BGX_CUDA(ctx, cudaMalloc(&plan->d_streams, ns * sizeof(StreamDev)));
+  if (!plan->h_streams.empty())
+    BGX_CUDA(ctx, cudaMemcpy(plan->d_streams, plan->h_streams.data(), plan->h_streams.size() * sizeof(StreamDev), cudaMemcpyHostToDevice));
+  BGX_CUDA(ctx, cudaMalloc(&plan->d_ctl, sizeof(QueueCtl)));
+  BGX_CUDA(ctx, cudaMalloc(&plan->d_status, std::max<size_t>(plan->total_pages, 1) * sizeof(uint32_t)));
+  plan->info.kernels_per_launch = (plan->total_pages ? 1u : 0u) + (uint32_t)plan->precon.size();
+  plan->info.sm_count = (uint32_t)ctx->sm_count;
+  plan->info.block_threads = 32;
+  plan->info.smem_bytes_per_block = (uint32_t)sizeof(bgxk::WarpSmem);
+  const uint64_t max_blocks = (uint64_t)ctx->sm_count * ctx->blocks_per_sm;
+  plan->info.grid_blocks = (uint32_t)std::min<uint64_t>(max_blocks, std::max<uint32_t>(plan->total_pages, 1));
+  guard.p = nullptr;
+  *out = plan;
+  return bgx::kOk;
+}
+
+int bgx_plan_launch(bgx_context* ctx, bgx_plan* plan, void* cuda_stream) {
+  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+  plan->last_stream = st;
+  BGX_CUDA(ctx, cudaMemsetAsync(plan->d_ctl, 0, sizeof(QueueCtl), st));
+  for (auto& p : plan->precon)
+    if (p.has_padding) BGX_CUDA(ctx, cudaMemsetAsync(p.d_tex, 0, p.out_size, st));   // pitch padding stays 0 (BrotligDecoder.cpp:448)
+  if (plan->total_pages) {
+    bgx_decode_pages_kernel<<<plan->info.grid_blocks, 32, 0, st>>>(plan->d_streams, (uint32_t)plan->h_streams.size(),
+                                                                   plan->total_pages, plan->d_ctl, plan->d_status);
+    BGX_CUDA(ctx, cudaGetLastError());
+  }
+  for (auto& p : plan->precon) {
+    const uint32_t blocks = (p.layout.total_blocks + 255u) / 256u;
+    if (blocks) bgx_decondition_kernel<<<blocks, 256, 0, st>>>(p.d_layout, p.d_planes, p.d_tex);
+    BGX_CUDA(ctx, cudaGetLastError());
+  }
+  return bgx::kOk;
+}
+
+int bgx_plan_finish(bgx_context* ctx, bgx_plan* plan, uint32_t* bad_pages) {
+  QueueCtl h{};
+  BGX_CUDA(ctx, cudaStreamSynchronize(plan->last_stream ? plan->last_stream : ctx->stream));
+  BGX_CUDA(ctx, cudaMemcpy(&h, plan->d_ctl, sizeof h, cudaMemcpyDeviceToHost));
+  if (bad_pages) *bad_pages = h.bad_pages;
+  if (h.bad_pages) { ctx->err = std::to_string(h.bad_pages) + " page(s) failed to decode"; return bgx::kErrCorruptStream; }
+  return bgx::kOk;
+}
+
+int bgx_decode_batch_host(bgx_context* ctx, uint32_t n, const uint8_t* const* inputs, const uint32_t* input_sizes,
+                          uint8_t* const* outputs, uint32_t* output_sizes, double* kernel_ms) {
+  BGX_CUDA(ctx, cudaSetDevice(ctx->device));
+  std::vector<bgx_stream> st(n);
+  std::vector<size_t> in_off(n), out_off(n);
+  std::vector<uint32_t> usize(n);
+  size_t in_total = 0, out_total = 0;
+  for (uint32_t i = 0; i < n; ++i) {
+    if (input_sizes[i] < bgx::kStreamHeaderBytes) { ctx->err = "stream shorter than its header"; return bgx::kErrCorruptStream; }
+    StreamInfo si;
+    const int rc = bgx::parse_stream_header(inputs[i], &si);
+    if (rc) return rc;
+    if (si.uncompressed_size > output_sizes[i]) { ctx->err = "output buffer too small"; return bgx::kErrGeneric; }
+    usize[i] = si.uncompressed_size;
+    in_off[i] = in_total;
+    in_total += ((size_t)input_sizes[i] + bgx::kInputSlackBytes + 255u) & ~(size_t)255u;
+    out_off[i] = out_total;
+    out_total += ((size_t)si.uncompressed_size + 255u) & ~(size_t)255u;
+  }
+  if (grow(ctx, &ctx->d_in, &ctx->d_in_cap, in_total)) return bgx::kErrGeneric;
+  if (grow(ctx, &ctx->d_out, &ctx->d_out_cap, out_total)) return bgx::kErrGeneric;
+  for (uint32_t i = 0; i < n; ++i) {
+    BGX_CUDA(ctx, cudaMemcpyAsync(ctx->d_in + in_off[i], inputs[i], input_sizes[i], cudaMemcpyHostToDevice, ctx->stream));
+    bgx_stream& s = st[i];
+    memset(&s, 0, sizeof s);
+    s.d_src = ctx->d_in + in_off[i];
+    s.src_size = input_sizes[i];
+    s.src_capacity = input_sizes[i];
+    s.d_dst = ctx->d_out + out_off[i];
+    s.dst_capacity = usize[i];
+    memcpy(s.header, inputs[i], std::min<uint32_t>(16, input_sizes[i]));
+  }
+  bgx_plan* plan = nullptr;
+  int rc = bgx_plan_create(ctx, st.data(), n, &plan);
+  if (rc) return rc;
+  cudaEventRecord(ctx->ev0, ctx->stream);
+  rc = bgx_plan_launch(ctx, plan, ctx->stream);
+  cudaEventRecord(ctx->ev1, ctx->stream);
+  if (!rc) {
+    for (uint32_t i = 0; i < n; ++i)
+      if (usize[i]) cudaMemcpyAsync(outputs[i], ctx->d_out + out_off[i], usize[i], cudaMemcpyDeviceToHost, ctx->stream);
+    rc = bgx_plan_finish(ctx, plan, nullptr);
+  }
+  if (!rc) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess && kernel_ms) *kernel_ms += ms;
+    for (uint32_t i = 0; i < n; ++i) output_sizes[i] = usize[i];
+  }
+  bgx_plan_destroy(plan);
+  return rc;
+}
+
+int bgx_decode_host(bgx_context* ctx, uint32_t input_size, const uint8_t* input, uint32_t* output_size, uint8_t* output,
+                    double* kernel_ms) {
+  const uint8_t* ins[1] = {input};
+  uint8_t* outs[1] = {output};
+  return bgx_decode_batch_host(ctx, 1, ins, &input_size, outs, output_size, kernel_ms);
+}
+
+}  // extern "C"

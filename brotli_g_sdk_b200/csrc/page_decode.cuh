@@ -1,0 +1,845 @@
+// page_decode.cuh -- the Brotli-G page decoder for sm_100a: ONE WARP DECODES ONE PAGE, lane = sub-stream.
+//
+// This is a from-scratch CUDA design (not a translation of src/decoder/BrotliGCompute.hlsl). What it
+// has to reproduce bit-for-bit is the behaviour of the reference CPU page decoder:
+//   PageDecoder::Run            /root/reference/src/decoder/PageDecoder.cpp:65-268
+//   LoadHuffmanTable            /root/reference/src/decoder/BrotligHuffmanTable.cpp:73-205
+//   DecodeCommand / Translate.. /root/reference/src/decoder/PageDecoder.cpp:290-404
+//   BrotligDeswizzler           /root/reference/inc/common/BrotligDeswizzler.h:43-206
+//
+// Design (see DESIGN.md for the full picture):
+//   * per-warp shared-memory arena (WarpSmem, ~13.6 KB): three LSB-first primary look-up tables
+//     (10/10/9 bits) + canonical "limit/base/sorted" arrays for the rare longer codes, a 1 KB literal
+//     ring, and a 4 KB output ring that write-combines the page before it goes to HBM as 16-byte
+//     coalesced stores. Near matches are served from the ring, far matches from L1/L2.
+//   * the bit reader of a lane is a 64-bit window (w0,w1) + one prefetched word, refilled with
+//     aligned 32-bit loads; a peek is a single funnel shift.
+//   * table build is warp-parallel: ballot/scan over the run-length coded code lengths, match_any
+//     ranking for the canonical order, cooperative LUT fill for short codes.
+//   * per round of <=32 commands: speculative command decode in every lane, warp scans for output
+//     and literal positions, parallel relaxation of the distance ring, lane-per-command literal
+//     inserts, then match copies in dependency "wavefronts" (a copy runs as soon as its source lies
+//     below the destination of the first still-pending copy).
+//   * rounds that produce more than kRoundMax bytes or need more literals than the literal ring
+//     holds (long runs) take a warp-cooperative path straight to global memory.
+//
+// The file is also compiled by g++ against tests/emul/warp_emul.h (BGX_EMULATED) so that the very
+// same code can be exercised on the CPU-only development box. That emulator is test infrastructure.
+#pragma once
+#include <stdint.h>
+
+#include "bgx_format.h"
+
+#ifndef BGX_EMULATED
+#include <cuda_runtime.h>
+#define BGX_DEV __device__ __forceinline__
+#define BGX_DEV_NOINLINE __device__ __noinline__
+#else
+#define BGX_DEV inline
+#define BGX_DEV_NOINLINE inline
+#endif
+
+namespace bgxk {
+
+constexpr unsigned kFull = 0xffffffffu;
+constexpr int kCmdLutBits = 10;
+constexpr int kLitLutBits = 10;
+constexpr int kDistLutBits = 9;
+constexpr uint32_t kLitQ = 1024;      // literal ring bytes (power of two, multiple of 32)
+constexpr uint32_t kRing = 4096;      // output ring bytes (power of two)
+constexpr uint32_t kRoundMax = 1024;  // largest round (bytes produced) the ring path accepts
+constexpr uint32_t kFlushChunk = 512; // 32 lanes x 16 B
+constexpr uint32_t kCoopLen = 32;     // inserts/copies at least this long are done by the whole warp
+constexpr uint16_t kLongCode = 0xffffu;  // primary-LUT marker: code longer than the LUT index
+
+// page status bits written to PageResult.status
+enum : uint32_t {
+  kPageOk = 0,
+  kPageErrOverrun = 1,      // commands produce more bytes than the page holds
+  kPageErrDistance = 2,     // distance 0 or reaching before the start of the page
+  kPageErrLiterals = 4,     // a round needs more literals than it carries
+  kPageErrTable = 8,        // malformed prefix-code description
+};
+
+struct HuffAux {
+  uint16_t limit[16];   // limit[L] = (first_code[L] + count[L]) << (15 - L): left-aligned exclusive upper bound
+  uint16_t base[16];    // base[L]  = offset_in_sorted[L] - first_code[L]   (mod 2^16)
+};
+
+struct WarpSmem {
+  uint16_t lut_cmd[1 << kCmdLutBits];
+  uint16_t lut_lit[1 << kLitLutBits];
+  uint16_t lut_dist[1 << kDistLutBits];
+  uint16_t sorted_cmd[bgx::kNumCmdSymbols];
+  uint16_t sorted_dist[bgx::kNumDistSymbols];
+  uint16_t sorted_lit[bgx::kNumLitSymbols];
+  HuffAux aux[3];
+  uint32_t lenlut[48];              // [0..23] insert code, [24..47] copy code: base | extra_bits << 16
+  uint32_t scratch[40];             // table build: cnt[16], next[16]; code-length code: 18 lengths
+  uint8_t litq[kLitQ];              // literal ring, indexed by page-global literal index; doubles as
+                                    // the 512 x u16 code-length-code LUT while tables are read
+  alignas(16) uint8_t ring[kRing];  // output ring; doubles as the code-length array while tables are read
+};
+
+// ---------------------------------------------------------------------------------------------
+// bit reader: lane-private, LSB first. Words are fetched from `base` (4-byte aligned start of the
+// page) with the index clamped to `lim` so that the deliberate over-read of the format
+// (BrotligDeswizzler.h:74-81) never leaves the stream buffer.
+struct BitRd {
+  uint32_t w0, w1, nxt;   // 64-bit window {w1:w0} and the prefetched next word
+  uint32_t bitpos;        // < 32 between operations
+  uint32_t off;           // word index of the word after `nxt`
+};
+
+struct PageIn {
+  const uint32_t* base;   // page start (4-byte aligned)
+  uint32_t lim;           // largest word index that may be loaded
+};
+
+BGX_DEV uint32_t ld_word(const PageIn& in, uint32_t idx) { return in.base[idx < in.lim ? idx : in.lim]; }
+
+BGX_DEV void br_init(BitRd& r, const PageIn& in, uint32_t byte_off) {
+  const uint32_t w = byte_off >> 2;
+  r.w0 = ld_word(in, w);
+  r.w1 = ld_word(in, w + 1);
+  r.nxt = ld_word(in, w + 2);
+  r.off = w + 3;
+  r.bitpos = (byte_off & 3u) * 8u;
+}
+BGX_DEV uint32_t br_peek(const BitRd& r) { return __funnelshift_r(r.w0, r.w1, r.bitpos); }  // 32 valid bits
+BGX_DEV void br_skip(BitRd& r, const PageIn& in, uint32_t n) {   // n <= 32
+  r.bitpos += n;
+  if (r.bitpos >= 32u) {
+    r.w0 = r.w1;
+    r.w1 = r.nxt;
+    r.nxt = ld_word(in, r.off);
+    r.off += 1;
+    r.bitpos -= 32u;
+  }
+}
+BGX_DEV uint32_t low_mask(uint32_t n) { return n >= 32u ? 0xffffffffu : ((1u << n) - 1u); }
+BGX_DEV uint32_t br_read(BitRd& r, const PageIn& in, uint32_t n) {   // n <= 32
+  const uint32_t v = br_peek(r) & low_mask(n);
+  br_skip(r, in, n);
+  return v;
+}
+
+BGX_DEV uint32_t lane_id() {
+#ifdef BGX_EMULATED
+  return (uint32_t)wemu::lane();
+#else
+  return threadIdx.x & 31u;
+#endif
+}
+
+BGX_DEV uint32_t warp_incl_scan(uint32_t v, uint32_t lane) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t t = __shfl_up_sync(kFull, v, d);
+    if (lane >= (uint32_t)d) v += t;
+  }
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// prefix-code decode: primary LUT entry = symbol | length << 10; kLongCode => canonical search.
+template <int BITS>
+BGX_DEV uint32_t huff_decode(const uint16_t* lut, const HuffAux& aux, const uint16_t* sorted, uint32_t nsym,
+                             uint32_t peek, uint32_t& len) {
+  const uint32_t e = lut[peek & ((1u << BITS) - 1u)];
+  if (e != kLongCode) {
+    len = e >> 10;
+    return e & 0x3ffu;
+  }
+  const uint32_t msb = __brev(peek) >> 17;   // first 15 stream bits as an MSB-first number
+  uint32_t L = BITS + 1;
+  while (L < 15u && msb >= aux.limit[L]) ++L;
+  len = L;
+  uint32_t idx = (uint16_t)(aux.base[L] + (msb >> (15u - L)));
+  if (idx >= nsym) idx = nsym - 1;
+  return sorted[idx];
+}
+
+// ---------------------------------------------------------------------------------------------
+// cooperative fill of the LUT entries owned by one code: all indices whose low `len` bits equal
+// `rev` (the bit-reversed code).
+template <int BITS>
+BGX_DEV void lut_fill_coop(uint16_t* lut, uint32_t rev, uint32_t len, uint16_t entry, uint32_t lane) {
+  for (uint32_t j = rev + (lane << len); j < (1u << BITS); j += (32u << len)) lut[j] = entry;
+}
+
+// Builds LUT + canonical arrays from the code lengths in `lens[0..n)` (shared memory).
+// Canonical order = (length, symbol index), as GenerateHuffmanTable (BrotligHuffmanTable.cpp:44-71).
+template <int BITS>
+BGX_DEV void build_table(WarpSmem* sm, const uint8_t* lens, uint32_t n, uint16_t* lut, HuffAux& aux, uint16_t* sorted,
+                         uint32_t lane) {
+  uint32_t* cnt = sm->scratch;        // [16]
+  uint32_t* next = sm->scratch + 16;  // [16] running position in `sorted` per length
+  if (lane < 16) cnt[lane] = 0;
+  __syncwarp();
+  for (uint32_t s = lane; s < n; s += 32) atomicAdd(&cnt[lens[s]], 1u);
+  __syncwarp();
+  if (lane == 0) {
+    uint32_t code = 0, off = 0;
+    cnt[0] = 0;
+    aux.limit[0] = 0;
+    aux.base[0] = 0;
+    for (uint32_t L = 1; L <= 15; ++L) {
+      code = (code + cnt[L - 1]) << 1;                   // first code of length L
+      aux.base[L] = (uint16_t)(off - code);
+      const uint32_t lim = (code + cnt[L]) << (15 - L);
+      aux.limit[L] = (uint16_t)(lim > 0x8000u ? 0x8000u : lim);
+      next[L] = off;
+      off += cnt[L];
+    }
+  }
+  __syncwarp();
+  for (uint32_t s0 = 0; s0 < n; s0 += 32) {
+    const uint32_t s = s0 + lane;
+    const uint32_t L = s < n ? lens[s] : 0u;
+    const uint32_t m = __match_any_sync(kFull, L);
+    const uint32_t rank = __popc(m & ((1u << lane) - 1u));
+    uint32_t idx = 0, code = 0;
+    if (L) {
+      idx = next[L] + rank;
+      code = (idx - aux.base[L]) & 0xffffu;
+    }
+    __syncwarp();
+    if (L && rank == 0) next[L] += __popc(m);
+    if (L) {
+      if (idx < n) sorted[idx] = (uint16_t)s;
+      if (L > (uint32_t)BITS) {
+        const uint32_t prefix = code >> (L - BITS);
+        lut[__brev(prefix) >> (32 - BITS)] = kLongCode;
+      }
+    }
+    // codes owning >= 32 LUT entries: whole warp fills them, one code at a time
+    uint32_t wide = __ballot_sync(kFull, L != 0 && L + 5 <= (uint32_t)BITS);
+    while (wide) {
+      const int k = __ffs(wide) - 1;
+      wide &= wide - 1;
+      const uint32_t Lk = __shfl_sync(kFull, L, k);
+      const uint32_t ck = __shfl_sync(kFull, code, k);
+      lut_fill_coop<BITS>(lut, __brev(ck) >> (32 - Lk), Lk, (uint16_t)((s0 + k) | (Lk << 10)), lane);
+    }
+    // the rest: each lane fills its own (<= 16) entries
+    if (L + 5 > (uint32_t)BITS && L <= (uint32_t)BITS) {
+      const uint16_t entry = (uint16_t)(s | (L << 10));
+      for (uint32_t j = __brev(code) >> (32 - L); j < (1u << BITS); j += (1u << L)) lut[j] = entry;
+    }
+    __syncwarp();
+  }
+}
+
+// Reads one prefix-code description (trivial / simple / complex) and builds its tables.
+// Returns 0 or kPageErrTable. Cursor conventions: every table starts at sub-stream 0 (lane 0).
+template <int BITS>
+BGX_DEV uint32_t load_table(WarpSmem* sm, BitRd& rd, const PageIn& in, uint32_t alphabet, uint16_t* lut, HuffAux& aux,
+                            uint16_t* sorted, uint32_t lane) {
+  const uint32_t max_bits = bgx::bit_length(alphabet - 1);
+  uint32_t hdr = 0;
+  if (lane == 0) hdr = br_read(rd, in, 6);
+  hdr = __shfl_sync(kFull, hdr, 0);
+  const uint32_t type = hdr & 3u;
+  if (type == 0) {  // trivial: one symbol, zero-length code (BrotligHuffmanTable.cpp:87-101)
+    uint32_t sym = 0;
+    if (lane == 0) sym = br_read(rd, in, max_bits);
+    sym = __shfl_sync(kFull, sym, 0);
+    for (uint32_t j = lane; j < (1u << BITS); j += 32) lut[j] = (uint16_t)sym;   // length field 0
+    __syncwarp();
+    return 0;
+  }
+  if (type == 1) {  // simple: 2..4 symbols, k-th symbol in sub-stream k, table filled in STORED order (:102-125)
+    const uint32_t nsym = ((hdr >> 2) & 3u) + 1u;
+    const uint32_t tree_select = (hdr >> 4) & 1u;
+    if (nsym < 2) return kPageErrTable;
+    uint32_t sym = 0;
+    if (lane < nsym) sym = br_read(rd, in, max_bits);
+    // shapes {1,1} {1,2,2} {2,2,2,2} {1,2,3,3}; codes are consecutive in stored order
+    const uint32_t shape = nsym < 4 ? nsym - 2 : (tree_select ? 3u : 2u);
+    const uint32_t lens4 = shape == 0 ? 0x0011u : shape == 1 ? 0x0221u : shape == 2 ? 0x2222u : 0x3321u;
+    const uint32_t codes4 = shape == 0 ? 0x0010u : shape == 1 ? 0x0320u : shape == 2 ? 0x3210u : 0x7620u;
+    for (uint32_t k = 0; k < nsym; ++k) {
+      const uint32_t sk = __shfl_sync(kFull, sym, k);
+      const uint32_t Lk = (lens4 >> (4 * k)) & 15u;
+      const uint32_t ck = (codes4 >> (4 * k)) & 15u;
+      lut_fill_coop<BITS>(lut, __brev(ck) >> (32 - Lk), Lk, (uint16_t)((sk & 0x3ffu) | (Lk << 10)), lane);
+    }
+    __syncwarp();
+    return 0;
+  }
+  if (type != 2) return kPageErrTable;
+
+  // ---- complex (:126-200). 1) code-length code: i-th 5-bit length in sub-stream i, storage order below.
+  const uint32_t ncl = ((hdr >> 2) & 15u) + 4u;
+  // order packed 5 bits each: 1,2,3,4,0,5,17,6,16,7,8,9,10,11,12,13,14,15
+  const uint32_t kOrder[18] = {1, 2, 3, 4, 0, 5, 17, 6, 16, 7, 8, 9, 10, 11, 12, 13, 14, 15};
+  uint32_t* cl_len_by_sym = sm->scratch + 16;   // [18] (next[] is not live yet)
+  uint16_t* cl_lut = reinterpret_cast<uint16_t*>(sm->litq);   // 512 entries: sym | len << 8
+  uint32_t myread = 0;
+  if (lane < 18) cl_len_by_sym[lane] = 0;   // the reference leaves these uninitialised when ncl < 18
+  __syncwarp();
+  if (lane < ncl && lane < 18) {
+    myread = br_read(rd, in, 5);
+    cl_len_by_sym[kOrder[lane]] = myread;
+  }
+  const uint32_t bad = __ballot_sync(kFull, myread > 9u);
+  if (bad) return kPageErrTable;   // reference: out-of-bounds table index
+  __syncwarp();
+  // canonical codes over symbols 0..ncl-1 (GenerateHuffmanTable is called with size = ncl, :145),
+  // but the per-length counts come from every length that was read (:135-142)
+  const uint32_t ls = (lane < ncl && lane < 18) ? cl_len_by_sym[lane] : 0u;
+  const uint32_t msame = __match_any_sync(kFull, ls);
+  const uint32_t rank = __popc(msame & ((1u << lane) - 1u));
+  uint32_t code = 0, mycode = 0, prevcnt = 0;
+  for (uint32_t L = 1; L <= 9; ++L) {
+    code = (code + prevcnt) << 1;
+    prevcnt = __popc(__ballot_sync(kFull, lane < ncl && lane < 18 && myread == L));
+    if (ls == L) mycode = code + rank;
+  }
+  for (uint32_t j = lane; j < 256; j += 32) reinterpret_cast<uint32_t*>(cl_lut)[j] = 0;   // sym 0, len 0
+  __syncwarp();
+  for (uint32_t k = 0; k < 18; ++k) {
+    const uint32_t Lk = __shfl_sync(kFull, ls, k);
+    const uint32_t ck = __shfl_sync(kFull, mycode, k);
+    if (Lk) lut_fill_coop<9>(cl_lut, (__brev(ck) >> (32 - Lk)) & 511u, Lk, (uint16_t)(k | (Lk << 8)), lane);
+  }
+  __syncwarp();
+
+  // ---- 2) the code lengths themselves: k-th code-length symbol lives in sub-stream k mod 32
+  uint8_t* lens = sm->ring;
+  uint32_t filled = 0, prev_carry = bgx::kInitialRepeatLen;
+  while (filled < alphabet) {
+    const uint32_t pk = br_peek(rd);
+    const uint32_t e = cl_lut[pk & 511u];
+    const uint32_t s = e & 0xffu, l = e >> 8;
+    uint32_t run = 1, nb = l;
+    if (s == (uint32_t)bgx::kRepeatPrev) { run = 3 + ((pk >> l) & 3u); nb = l + 2; }
+    else if (s == (uint32_t)bgx::kRepeatZero) { run = 3 + ((pk >> l) & 7u); nb = l + 3; }
+    const uint32_t incl = warp_incl_scan(run, lane);
+    const uint32_t start = filled + incl - run;
+    const bool active = start < alphabet;   // otherwise this symbol does not exist: consume nothing
+    const uint32_t expl = __ballot_sync(kFull, active && s < 16u);
+    const uint32_t below = expl & ((1u << lane) - 1u);
+    const uint32_t pv = __shfl_sync(kFull, s, below ? (31 - __clz((int)below)) : 0);
+    const uint32_t prevval = below ? pv : prev_carry;
+    const uint32_t val = s == (uint32_t)bgx::kRepeatPrev ? prevval : (s == (uint32_t)bgx::kRepeatZero ? 0u : s);
+    if (active) {
+      for (uint32_t k = 0; k < run && start + k < alphabet; ++k) lens[start + k] = (uint8_t)val;
+      br_skip(rd, in, nb);
+    }
+    if (expl) prev_carry = __shfl_sync(kFull, s, 31 - __clz((int)expl));
+    else (void)__shfl_sync(kFull, s, 0);
+    filled += __reduce_add_sync(kFull, active ? run : 0u);
+  }
+  __syncwarp();
+  build_table<BITS>(sm, lens, alphabet, lut, aux, sorted, lane);
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+struct PageJob {
+  const uint8_t* in;        // compressed page (4-byte aligned)
+  uint32_t in_size;
+  uint32_t in_limit;        // bytes readable from `in` (to the end of the stream buffer incl. slack), >= in_size
+  uint8_t* out;             // where this page's bytes go
+  uint32_t out_size;
+  uint32_t allow_delta;     // stream is preconditioned (page delta flag is honoured, PageDecoder.cpp:87)
+};
+
+struct PageResult {
+  uint32_t status;          // kPage* bits
+  uint32_t is_delta;        // page header flag (&& allow_delta)
+};
+
+// read one output byte of the current page at position p (< current write position)
+BGX_DEV uint8_t out_byte(const WarpSmem* sm, const uint8_t* out, int32_t ring_lo, uint32_t p) {
+  return ((int32_t)p >= ring_lo) ? sm->ring[p & (kRing - 1)] : out[p];
+}
+
+// write ring bytes [from, to) to global memory; byte granular, coalesced
+BGX_DEV void flush_bytes(const WarpSmem* sm, uint8_t* out, uint32_t from, uint32_t to, uint32_t lane) {
+  for (uint32_t p = from + lane; p < to; p += 32) out[p] = sm->ring[p & (kRing - 1)];
+}
+
+// Decodes `cnt` literals in this lane (lane-dependent count allowed) into the literal ring at
+// page-global literal indices tail + j*32 + lane.
+BGX_DEV void decode_literals(WarpSmem* sm, BitRd& rd, const PageIn& in, uint32_t tail, uint32_t cnt, uint32_t lane) {
+  uint32_t q = (tail + lane) & (kLitQ - 1);
+  for (uint32_t j = 0; j < cnt; ++j) {
+    uint32_t len;
+    const uint32_t sym = huff_decode<kLitLutBits>(sm->lut_lit, sm->aux[2], sm->sorted_lit, bgx::kNumLitSymbols,
+                                                  br_peek(rd), len);
+    sm->litq[q] = (uint8_t)sym;
+    q = (q + 32) & (kLitQ - 1);
+    br_skip(rd, in, len);
+  }
+}
+
+// The page decoder. All 32 lanes of the warp call it with identical arguments.
+BGX_DEV_NOINLINE PageResult decode_page_warp(const PageJob& job, WarpSmem* sm) {
+  const uint32_t lane = lane_id();
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  PageResult res;
+  res.status = kPageOk;
+  res.is_delta = 0;
+
+  PageIn in;
+  in.base = reinterpret_cast<const uint32_t*>(job.in);
+  in.lim = (job.in_limit >> 2) ? (job.in_limit >> 2) - 1 : 0;
+
+  // ---- length-code tables (RFC 7932 section 5)
+  if (lane < 24) {
+    sm->lenlut[lane] = bgx::insert_base(lane) | (bgx::insert_extra_bits(lane) << 16);
+    sm->lenlut[24 + lane] = bgx::copy_base(lane) | (bgx::copy_extra_bits(lane) << 16);
+  }
+
+  // ---- page header + sub-stream size table (PageDecoder.cpp:79-121): every lane parses the header
+  //      words it needs itself (they are the first few words of the page: broadcast loads)
+  uint32_t npostfix, ndirect, sub_off;
+  {
+    auto hdr_bits = [&](uint32_t pos, uint32_t n) -> uint32_t {   // n <= 25
+      const uint32_t w = pos >> 5, b = pos & 31u;
+      const uint32_t lo = ld_word(in, w), hi = ld_word(in, w + 1);
+      return __funnelshift_r(lo, hi, b) & low_mask(n);
+    };
+    npostfix = hdr_bits(0, 2);
+    ndirect = hdr_bits(2, 4) << npostfix;
+    res.is_delta = hdr_bits(6, 1) && job.allow_delta;
+    const uint32_t base_bits = bgx::floor_log2((job.in_size + 31u) / 32u) + 1u;
+    const uint32_t dbits_bits = bgx::floor_log2(bgx::floor_log2(job.in_size - 1u) + 1u) + 1u;
+    const uint32_t base_size = hdr_bits(8, base_bits);
+    const uint32_t delta_bits = hdr_bits(8 + base_bits, dbits_bits);
+    const uint32_t tbl = 8 + base_bits + dbits_bits;
+    const uint32_t hdr_bytes = ((tbl + 32u * delta_bits + 31u) / 32u) * 4u;
+    const uint32_t dmine = delta_bits ? hdr_bits(tbl + lane * delta_bits, delta_bits > 25 ? 25 : delta_bits) : 0u;
+    const uint32_t mysize = base_size + dmine;
+    sub_off = hdr_bytes + warp_incl_scan(mysize, lane) - mysize;
+  }
+  BitRd rd;
+  br_init(rd, in, sub_off);
+  __syncwarp();
+
+  // ---- the three prefix codes: insert&copy (728), distance (544), literal (256)  (PageDecoder.cpp:126-147)
+  uint32_t terr = load_table<kCmdLutBits>(sm, rd, in, bgx::kNumCmdSymbols, sm->lut_cmd, sm->aux[0], sm->sorted_cmd, lane);
+  if (!terr) terr = load_table<kDistLutBits>(sm, rd, in, bgx::kNumDistSymbols, sm->lut_dist, sm->aux[1], sm->sorted_dist, lane);
+  if (!terr) terr = load_table<kLitLutBits>(sm, rd, in, bgx::kNumLitSymbols, sm->lut_lit, sm->aux[2], sm->sorted_lit, lane);
+  if (terr) { res.status = terr; return res; }
+  __syncwarp();
+
+  // ---- decode state (all uniform across the warp unless noted)
+  uint8_t* const out = job.out;
+  const uint32_t out_size = job.out_size;
+  const bool out_aligned = (reinterpret_cast<uintptr_t>(out) & 15u) == 0;
+  uint32_t pos = 0;            // bytes of the page produced so far
+  uint32_t flushed = 0;        // bytes already in global memory
+  int32_t ring_from = 0;       // ring holds valid data for positions >= ring_from (and > end - kRing)
+  uint32_t lit_head = 0;       // page-global literal index of the next literal to emit
+  uint32_t lit_tail = 0;       // literals decoded so far
+  uint32_t r0 = 4, r1 = 11, r2 = 15, r3 = 16;   // distance ring (PageDecoder.cpp:150-153)
+  uint32_t err = 0;
+  bool done = false;
+
+  while (!done) {
+    // ================= 1. one command per lane, speculatively (lanes after the sentinel roll back)
+    BitRd r = rd;
+    uint32_t len;
+    uint32_t sym = huff_decode<kCmdLutBits>(sm->lut_cmd, sm->aux[0], sm->sorted_cmd, bgx::kNumCmdSymbols, br_peek(r), len);
+    br_skip(r, in, len);
+    const uint32_t sent = __ballot_sync(kFull, sym == (uint32_t)bgx::kCmdSentinel);
+    const uint32_t n = sent ? (uint32_t)(__ffs((int)sent) - 1) : 32u;   // commands in this round
+    done = sent != 0;
+    uint32_t ins = 0, cpy = 0, dcode = 0, dist = 0;
+    bool has_copy = false;
+    if (lane < n) {
+      uint32_t ic, cc = 0;
+      if (sym < (uint32_t)bgx::kCmdSentinel) {
+        ic = bgx::icp_insert_code(sym);
+        cc = bgx::icp_copy_code(sym);
+        has_copy = true;
+      } else {
+        ic = sym - (uint32_t)bgx::kCmdSentinel;      // insert-only (PageDecoder.cpp:308-317)
+        if (ic > 23u) ic = 23u;
+      }
+      const uint32_t ei = sm->lenlut[ic];
+      ins = (ei & 0xffffu) + br_read(r, in, ei >> 16);
+      if (has_copy) {
+        const uint32_t ec = sm->lenlut[24 + cc];
+        cpy = (ec & 0xffffu) + br_read(r, in, ec >> 16);
+        if (sym >= 128u) {
+          dcode = huff_decode<kDistLutBits>(sm->lut_dist, sm->aux[1], sm->sorted_dist, bgx::kNumDistSymbols, br_peek(r), len);
+          br_skip(r, in, len);
+        }
+        if (dcode >= 16u) {   // explicit distance (PageDecoder.cpp:367-394)
+          if (ndirect > 0 && dcode < 16u + ndirect) {
+            dist = dcode - 15u;
+          } else {
+            const uint32_t v = dcode - ndirect - 16u;
+            uint32_t nb = 1u + (v >> (npostfix + 1u));
+            if (nb > 24u) nb = 24u;
+            const uint32_t extra = br_read(r, in, nb);
+            const uint32_t h = v >> npostfix, lo = v & ((1u << npostfix) - 1u);
+            dist = ((((2u + (h & 1u)) << nb) - 4u + extra) << npostfix) + lo + ndirect + 1u;
+          }
+        }
+      }
+      rd = r;
+    } else if (lane == n) {
+      rd = r;   // the sentinel's code bits are consumed; its lane then continues with literals
+    }
+
+    // ================= 2. positions
+    const uint32_t tot = ins + cpy;
+    const uint32_t incl_tot = warp_incl_scan(tot, lane);
+    const uint32_t incl_ins = warp_incl_scan(ins, lane);
+    const uint32_t round_out = __shfl_sync(kFull, incl_tot, 31);
+    const uint32_t round_ins = __shfl_sync(kFull, incl_ins, 31);
+    const uint32_t o_ins = pos + incl_tot - tot;        // where this command's literals go
+    const uint32_t o_cpy = o_ins + ins;                 // where its copy goes
+    const uint32_t lq = lit_head + incl_ins - ins;      // page-global index of its first literal
+    if (round_out > out_size - pos) { err = kPageErrOverrun; break; }
+    const uint32_t round_end = pos + round_out;
+
+    // ================= 3. distance ring, resolved by relaxation (PageDecoder.cpp:345-404)
+    {
+      const uint32_t push = __ballot_sync(kFull, has_copy && dcode != 0);   // commands that enter the ring
+      const uint32_t below = push & lt_mask;
+      bool unresolved = has_copy && dcode < 16u;
+      // which ring slot (0..3) the short code refers to, and the offset applied to it
+      uint32_t slot = 0;
+      int32_t delta = 0;
+      if (unresolved) {
+        if (dcode < 4u) slot = dcode;
+        else {
+          const uint32_t c = dcode - 4u;              // 0..11
+          slot = c >= 6u ? 1u : 0u;
+          const uint32_t k = c >= 6u ? c - 6u : c;    // 0..5 => -1 +1 -2 +2 -3 +3
+          delta = (int32_t)(k >> 1) + 1;
+          if (!(k & 1u)) delta = -delta;
+        }
+      }
+      // source: the slot-th most recent pusher below me, else the carried ring
+      uint32_t b = below;
+      for (uint32_t k = 0; k < slot && b; ++k) b &= ~(1u << (31 - __clz((int)b)));
+      const uint32_t npush_below = __popc(below);
+      const bool from_carry = slot >= npush_below;
+      const uint32_t src_lane = from_carry ? 0u : (uint32_t)(31 - __clz((int)b));
+      const uint32_t cslot = slot - (from_carry ? npush_below : 0u);
+      const uint32_t carry_val = cslot == 0 ? r0 : cslot == 1 ? r1 : cslot == 2 ? r2 : r3;
+      uint32_t resolved = __ballot_sync(kFull, !unresolved);
+      while (resolved != kFull) {
+        const uint32_t v = __shfl_sync(kFull, dist, src_lane);
+        const bool ready = unresolved && (from_carry || ((resolved >> src_lane) & 1u));
+        if (ready) {
+          dist = (uint32_t)((int32_t)(from_carry ? carry_val : v) + delta);
+          unresolved = false;
+        }
+        resolved = __ballot_sync(kFull, !unresolved);
+      }
+      // new carried ring = four most recent pushers of this round, then the old ring
+      uint32_t pb = push;
+      uint32_t nr[4];
+      uint32_t old_idx = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t hb = pb ? (uint32_t)(31 - __clz((int)pb)) : 0u;
+        const uint32_t v = __shfl_sync(kFull, dist, hb);
+        if (pb) { nr[k] = v; pb &= ~(1u << hb); }
+        else { nr[k] = old_idx == 0 ? r0 : old_idx == 1 ? r1 : old_idx == 2 ? r2 : r3; ++old_idx; }
+      }
+      r0 = nr[0]; r1 = nr[1]; r2 = nr[2]; r3 = nr[3];
+      const uint32_t baddist = __ballot_sync(kFull, has_copy && (dist == 0 || dist > o_cpy));
+      if (baddist) { err = kPageErrDistance; break; }
+    }
+
+    // ================= 4. literals of this round (PageDecoder.cpp:196-206)
+    const uint32_t avail = lit_tail - lit_head;     // decoded ahead of need in earlier rounds (< 32)
+    const uint32_t need = round_ins > avail ? round_ins - avail : 0u;
+    const uint32_t mult = n ? (n == 32u ? (need + 31u) >> 5 : (need + n - 1u) / n) : 0u;
+    const uint32_t rl = n * mult;                   // literals the stream carries for this round
+    // lane's share: literal indices lit_tail + j*32 + lane < lit_tail + rl
+    uint32_t mine = rl > lane ? (rl - lane + 31u) >> 5 : 0u;
+    const bool fast = round_out <= kRoundMax && avail + rl <= kLitQ;
+
+    if (fast) {
+      decode_literals(sm, rd, in, lit_tail, mine, lane);
+      lit_tail += rl;
+      __syncwarp();
+      const int32_t ring_lo = ring_from > (int32_t)round_end - (int32_t)kRing ? ring_from : (int32_t)round_end - (int32_t)kRing;
+
+      // ---- 5. inserts: short ones lane-per-command, long ones by the whole warp
+      if (ins && ins < kCoopLen) {
+        uint32_t q = lq & (kLitQ - 1), p = o_ins & (kRing - 1);
+        for (uint32_t j = 0; j < ins; ++j) {
+          sm->ring[p] = sm->litq[q];
+          q = (q + 1) & (kLitQ - 1);
+          p = (p + 1) & (kRing - 1);
+        }
+      }
+      uint32_t big = __ballot_sync(kFull, ins >= kCoopLen);
+      while (big) {
+        const int k = __ffs((int)big) - 1;
+        big &= big - 1;
+        const uint32_t n_k = __shfl_sync(kFull, ins, k);
+        const uint32_t o_k = __shfl_sync(kFull, o_ins, k);
+        const uint32_t q_k = __shfl_sync(kFull, lq, k);
+        for (uint32_t j = lane; j < n_k; j += 32) sm->ring[(o_k + j) & (kRing - 1)] = sm->litq[(q_k + j) & (kLitQ - 1)];
+      }
+      __syncwarp();
+
+      // ---- 6. copies in dependency wavefronts
+      const uint32_t src_lo = o_cpy - dist;                              // first source byte
+      const uint32_t src_hi = src_lo + (cpy < dist ? cpy : dist);        // one past the last distinct source byte
+      uint32_t pending = __ballot_sync(kFull, cpy != 0);
+      while (pending) {
+        const int first = __ffs((int)pending) - 1;
+        const uint32_t hwm = __shfl_sync(kFull, o_cpy, first);           // everything below is final
+        const bool ready = ((pending >> lane) & 1u) && ((int)lane == first || src_hi <= hwm);
+        if (ready && cpy < kCoopLen) {
+          // byte-serial, so an overlapping copy (dist < len) replicates its pattern exactly as
+          // PageDecoder.cpp:222-232 does: later bytes read what this loop has just written
+          for (uint32_t j = 0; j < cpy; ++j)
+            sm->ring[(o_cpy + j) & (kRing - 1)] = out_byte(sm, out, ring_lo, src_lo + j);
+        }
+        const uint32_t ready_mask = __ballot_sync(kFull, ready);
+        uint32_t bigc = __ballot_sync(kFull, ready && cpy >= kCoopLen);
+        __syncwarp();
+        while (bigc) {
+          const int k = __ffs((int)bigc) - 1;
+          bigc &= bigc - 1;
+          const uint32_t n_k = __shfl_sync(kFull, cpy, k);
+          const uint32_t o_k = __shfl_sync(kFull, o_cpy, k);
+          const uint32_t d_k = __shfl_sync(kFull, dist, k);
+          const uint32_t s_k = o_k - d_k;
+          // byte j of the copy = pattern byte (j mod dist) of the dist bytes preceding the destination
+          for (uint32_t j = lane; j < n_k; j += 32) {
+            const uint32_t m = j < d_k ? j : j % d_k;
+            sm->ring[(o_k + j) & (kRing - 1)] = out_byte(sm, out, ring_lo, s_k + m);
+          }
+          __syncwarp();
+        }
+        pending &= ~ready_mask;
+      }
+      pos = round_end;
+      lit_head += round_ins;
+      // ---- 7. write-combined flush of complete 512-byte chunks
+      if (pos - flushed >= kFlushChunk) {
+        if (out_aligned) {
+          if (flushed & 15u) {   // after a cooperative (direct) episode the flush point may be unaligned
+            const uint32_t to = (flushed + 15u) & ~15u;
+            flush_bytes(sm, out, flushed, to, lane);
+            flushed = to;
+          }
+          while (pos - flushed >= kFlushChunk) {
+            const uint32_t p = flushed + 16u * lane;
+            *reinterpret_cast<uint4*>(out + p) = *reinterpret_cast<const uint4*>(&sm->ring[p & (kRing - 1)]);
+            flushed += kFlushChunk;
+          }
+        } else {
+          const uint32_t to = flushed + ((pos - flushed) / kFlushChunk) * kFlushChunk;
+          flush_bytes(sm, out, flushed, to, lane);
+          flushed = to;
+        }
+        __syncwarp();
+      }
+    } else {
+      // ================= slow path: long runs, straight to global memory, command by command
+      flush_bytes(sm, out, flushed, pos, lane);
+      flushed = pos;
+      __syncwarp();
+      for (uint32_t k = 0; k < n; ++k) {
+        uint32_t n_ins = __shfl_sync(kFull, ins, (int)k);
+        const uint32_t n_cpy = __shfl_sync(kFull, cpy, (int)k);
+        const uint32_t d_k = __shfl_sync(kFull, dist, (int)k);
+        while (n_ins) {
+          uint32_t have = lit_tail - lit_head;
+          if (have == 0) {
+            // decode the next chunk of this round's literals (as many as the literal ring takes)
+            const uint32_t room = (kLitQ - have) >> 5;
+            const uint32_t c = mine < room ? mine : room;
+            const uint32_t total = __reduce_add_sync(kFull, c);
+            if (total == 0) { err = kPageErrLiterals; break; }
+            decode_literals(sm, rd, in, lit_tail, c, lane);
+            mine -= c;
+            lit_tail += total;
+            __syncwarp();
+            have = lit_tail - lit_head;
+          }
+          const uint32_t take = n_ins < have ? n_ins : have;
+          for (uint32_t j = lane; j < take; j += 32) out[pos + j] = sm->litq[(lit_head + j) & (kLitQ - 1)];
+          pos += take;
+          lit_head += take;
+          n_ins -= take;
+          __syncwarp();
+        }
+        if (err) break;
+        if (n_cpy) {
+          const uint32_t s_k = pos - d_k;
+          for (uint32_t j = lane; j < n_cpy; j += 32) {
+            const uint32_t m = j < d_k ? j : j % d_k;
+            out[pos + j] = out[s_k + m];
+          }
+          pos += n_cpy;
+          __syncwarp();
+        }
+      }
+      if (err) break;
+      // literals the round still carries (decoded ahead of need, at most 31 remain unused)
+      while (__reduce_add_sync(kFull, mine) != 0) {
+        const uint32_t room = (kLitQ - (lit_tail - lit_head)) >> 5;
+        const uint32_t c = mine < room ? mine : room;
+        const uint32_t total = __reduce_add_sync(kFull, c);
+        if (total == 0) { err = kPageErrLiterals; break; }
+        decode_literals(sm, rd, in, lit_tail, c, lane);
+        mine -= c;
+        lit_tail += total;
+        __syncwarp();
+      }
+      if (err) break;
+      flushed = pos;
+      ring_from = (int32_t)pos;
+    }
+  }
+
+  // ---- tail: whatever is still only in the ring, then zero-fill (reference memsets the page first)
+  if (!err) {
+    flush_bytes(sm, out, flushed, pos, lane);
+    for (uint32_t p = pos + lane; p < out_size; p += 32) out[p] = 0;
+  }
+  __syncwarp();
+  res.status = err;
+  return res;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Pre-conditioned streams (BC1..BC5 textures). Pages decode into a scratch buffer that holds the
+// *conditioned* layout (one plane per block field); then
+//   1. delta_decode_warp  -- per page, in place: byte prefix sums over the colour end-point planes
+//                            (PageDecoder::DeltaDecode, PageDecoder.cpp:446-471), restarted per page;
+//   2. decondition_block  -- gathers the fields of one block from the planes and writes the block at
+//                            its texture address (inverse of PageDecoder::DeconditionBC1_5,
+//                            PageDecoder.cpp:406-444, which scatters byte by byte).
+struct DeltaPlanes {
+  uint32_t count;          // colour planes (0..4)
+  uint32_t lo[4], hi[4];   // [lo, hi) of each plane in the conditioned buffer
+};
+
+BGX_DEV void delta_decode_warp(uint8_t* page, uint32_t page_start, uint32_t page_size, const DeltaPlanes& dp) {
+  const uint32_t lane = lane_id();
+  const uint32_t page_end = page_start + page_size;
+  for (uint32_t i = 0; i < dp.count; ++i) {
+    const uint32_t cs = dp.lo[i], ce = dp.hi[i];
+    if (!(cs < page_end && page_start < ce)) continue;
+    const uint32_t a = cs > page_start ? cs - page_start : 0u;
+    const uint32_t b = ce < page_end ? ce - page_start : page_size;
+    uint32_t carry = 0;
+    for (uint32_t base = a; base < b; base += 128u) {
+      const uint32_t i0 = base + 4u * lane;
+      uint32_t y[4];
+      uint32_t run = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t x = (i0 + k < b) ? page[i0 + k] : 0u;
+        run = (run + x) & 0xffu;
+        y[k] = run;
+      }
+      const uint32_t incl = warp_incl_scan(run, lane);
+      const uint32_t add = carry + incl - run;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (i0 + k < b) page[i0 + k] = (uint8_t)(y[k] + add);
+      carry = (carry + __shfl_sync(kFull, incl, 31)) & 0xffu;
+    }
+    __syncwarp();
+  }
+}
+
+// Gathers block `t` (index in conditioned plane order over all mips) and writes it to the texture.
+BGX_HD void decondition_block(const bgx::PreconLayout& L, uint32_t t, const uint8_t* planes, uint8_t* tex) {
+  uint32_t mip = 0;
+  while (mip + 1 < L.num_mips && t >= L.mip_off_blocks[mip + 1]) ++mip;
+  const uint32_t block = t - L.mip_off_blocks[mip];
+  const uint32_t W = L.width_blocks[mip], H = L.height_blocks[mip];
+  uint32_t row = block / W, col = block - row * W;
+  if (L.swizzle && W >= 2 && H >= 2) {
+    const uint32_t remW = W & 1u, effW = W - remW, effH = H - (H & 1u);
+    if (row < effH && col < effW) {   // undo the 2x2 block-group swizzle
+      const uint32_t eff_block = block - row * remW;
+      const uint32_t grp = eff_block >> 2, in_grp = eff_block & 3u;
+      const uint32_t gpr = effW >> 1;
+      row = 2u * (grp / gpr) + (in_grp >> 1);
+      col = 2u * (grp % gpr) + (in_grp & 1u);
+    }
+  }
+  uint8_t* dst = tex + L.mip_off_bytes[mip] + row * L.pitch_bytes[mip] + col * L.block_bytes;
+  for (uint32_t sub = 0; sub < L.num_sub; ++sub) {
+    const uint32_t sz = L.sub_size[sub];
+    const uint8_t* src = planes + L.sub_stream_off[sub] + t * sz;
+    for (uint32_t k = 0; k < sz; ++k) dst[L.sub_off[sub] + k] = src[k];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// raw page (compressed size == uncompressed size, PageDecoder.cpp:70-76): a straight copy.
+BGX_DEV void copy_page_warp(uint8_t* dst, const uint8_t* src, uint32_t n) {
+  const uint32_t lane = lane_id();
+  const uintptr_t a = reinterpret_cast<uintptr_t>(dst), b = reinterpret_cast<uintptr_t>(src);
+  uint32_t i = 0;
+  if (((a | b) & 15u) == 0) {
+    const uint4* s = reinterpret_cast<const uint4*>(src);
+    uint4* d = reinterpret_cast<uint4*>(dst);
+    const uint32_t nv = n >> 4;
+    uint32_t v = lane;
+    for (; v + 7 * 32 < nv; v += 8 * 32) {
+      uint4 t[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) t[u] = s[v + u * 32];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) d[v + u * 32] = t[u];
+    }
+    for (; v < nv; v += 32) d[v] = s[v];
+    i = nv << 4;
+  } else if (((a & 15u) == 0) && ((b & 7u) == 0)) {
+    // typical stream layout: page data sits 8 bytes off a 16-byte boundary (8-byte header + 4n-byte table)
+    const uint2* s = reinterpret_cast<const uint2*>(src);
+    uint4* d = reinterpret_cast<uint4*>(dst);
+    const uint32_t nv = n >> 4;
+    uint32_t v = lane;
+    for (; v + 7 * 32 < nv; v += 8 * 32) {
+      uint2 t[16];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { t[2 * u] = s[2 * (v + u * 32)]; t[2 * u + 1] = s[2 * (v + u * 32) + 1]; }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        uint4 w;
+        w.x = t[2 * u].x; w.y = t[2 * u].y; w.z = t[2 * u + 1].x; w.w = t[2 * u + 1].y;
+        d[v + u * 32] = w;
+      }
+    }
+    for (; v < nv; v += 32) {
+      const uint2 lo = s[2 * v], hi = s[2 * v + 1];
+      uint4 w;
+      w.x = lo.x; w.y = lo.y; w.z = hi.x; w.w = hi.y;
+      d[v] = w;
+    }
+    i = nv << 4;
+  } else if (((a | b) & 3u) == 0) {
+    const uint32_t* s = reinterpret_cast<const uint32_t*>(src);
+    uint32_t* d = reinterpret_cast<uint32_t*>(dst);
+    const uint32_t nv = n >> 2;
+    uint32_t v = lane;
+    for (; v + 3 * 32 < nv; v += 4 * 32) {
+      uint32_t t[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) t[u] = s[v + u * 32];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) d[v + u * 32] = t[u];
+    }
+    for (; v < nv; v += 32) d[v] = s[v];
+    i = nv << 2;
+  }
+  for (uint32_t j = i + lane; j < n; j += 32) dst[j] = src[j];
+}
+
+}  // namespace bgxk

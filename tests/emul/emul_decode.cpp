@@ -1,0 +1,57 @@
+// tests/emul/emul_decode.cpp -- TEST INFRASTRUCTURE ONLY.
+// Runs the device code of brotli_g_sdk_b200/csrc/page_decode.cuh on the CPU warp emulator
+// (warp_emul.h), one emulated warp per page, so kernel logic can be checked without a GPU.
+#include "warp_emul.h"
+// clang-format off
+#include "../../brotli_g_sdk_b200/csrc/page_decode.cuh"
+#include "../../brotli_g_sdk_b200/csrc/host_plan.h"
+// clang-format on
+#include <vector>
+
+extern "C" {
+
+// Decodes every page of a (non-preconditioned view of a) stream. For preconditioned streams the
+// output is the *conditioned* byte plane sequence (before delta decode and de-conditioning).
+// status_out[page] receives the kernel status, flags_out[page] the delta flag. Returns a BROTLIG_ERROR.
+int emul_decode_stream(const uint8_t* src, uint32_t src_size, uint8_t* dst, uint32_t dst_capacity, uint32_t* status_out,
+                       uint32_t* flags_out, uint64_t* collectives_out) {
+  bgx::StreamInfo si;
+  const int rc = bgx::parse_stream_header(src, &si);
+  if (rc) return rc;
+  if (si.uncompressed_size > dst_capacity) return bgx::kErrGeneric;
+  const uint8_t* table = src + si.header_bytes;
+  const uint8_t* pages = table + 4 * (size_t)si.num_pages;
+  bgxk::WarpSmem* sm = new bgxk::WarpSmem();
+  memset(sm, 0xCD, sizeof(*sm));
+  uint64_t coll = 0;
+  int worst = 0;
+  for (uint32_t p = 0; p < si.num_pages; ++p) {
+    const bgx::PageExtent e = bgx::page_extent(si, table, p);
+    bgxk::PageResult res{0, 0};
+    if (e.in_size == e.out_size) {
+      coll += wemu::run_warp([&] { bgxk::copy_page_warp(dst + e.out_off, pages + e.in_off, e.out_size); });
+    } else {
+      bgxk::PageJob job;
+      job.in = pages + e.in_off;
+      job.in_size = e.in_size;
+      job.in_limit = (uint32_t)((src + src_size) - (pages + e.in_off));
+      job.out = dst + e.out_off;
+      job.out_size = e.out_size;
+      job.allow_delta = si.preconditioned;
+      bgxk::PageResult results[32];
+      coll += wemu::run_warp([&] { results[wemu::lane()] = bgxk::decode_page_warp(job, sm); });
+      res = results[0];
+      for (int l = 1; l < 32; ++l)
+        if (results[l].status != res.status || results[l].is_delta != res.is_delta) res.status |= 0x80000000u;
+    }
+    if (status_out) status_out[p] = res.status;
+    if (flags_out) flags_out[p] = res.is_delta;
+    if (res.status) worst = bgx::kErrCorruptStream;
+  }
+  delete sm;
+  if (collectives_out) *collectives_out = coll;
+  return worst;
+}
+
+uint32_t emul_warp_smem_bytes() { return (uint32_t)sizeof(bgxk::WarpSmem); }
+}

@@ -1,0 +1,295 @@
+// tests/emul/warp_emul.h -- TEST INFRASTRUCTURE ONLY.
+//
+// A single-warp SIMT emulator that lets the *same* device code that nvcc compiles for sm_100a
+// (brotli_g_sdk_b200/csrc/page_decode.cuh) be compiled with g++ and executed on the CPU, one page per
+// emulated warp. There is no GPU in the development container, so this is how kernel logic is
+// exercised before it is sent to a B200; it is never part of the product path.
+//
+// Model: 32 lanes = 32 cooperative fibers (ucontext) on one OS thread. A lane runs until it reaches
+// a warp collective (__shfl_sync, __ballot_sync, __syncwarp, ...), parks there, and the collective
+// completes when all 32 lanes have arrived. Lanes therefore run far "out of lock-step" between
+// collectives, which makes a missing __syncwarp() show up as a wrong answer instead of hiding it.
+// Restrictions (checked): every collective uses the full mask and is reached by all 32 lanes.
+#pragma once
+#include <ucontext.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+
+#define __device__
+#define __host__
+#define __global__
+#define __forceinline__ inline
+#define __noinline__
+#define __restrict__
+#define __launch_bounds__(...)
+#define BGX_EMULATED 1
+
+namespace wemu {
+
+enum Op : int { OP_NONE = 0, OP_SHFL, OP_SHFL_UP, OP_SHFL_DOWN, OP_SHFL_XOR, OP_BALLOT, OP_SYNC, OP_MATCH, OP_REDUCE };
+
+struct Warp {
+  ucontext_t sched;
+  ucontext_t ctx[32];
+  char* stack[32];
+  bool done[32];
+  int cur = 0;
+  // collective rendezvous
+  uint64_t slot[32];
+  uint32_t aux[32];
+  int op[32];
+  int arrived = 0;
+  uint64_t gen = 0;
+  uint64_t result[2][32];
+  uint32_t result_aux[2][32];
+  uint64_t collectives = 0;
+  std::function<void()> body;
+};
+
+inline Warp*& W() {
+  static thread_local Warp* w = nullptr;
+  return w;
+}
+inline int lane() { return W()->cur; }
+
+inline void yield_to_sched() {
+  Warp* w = W();
+  swapcontext(&w->ctx[w->cur], &w->sched);
+}
+
+// All 32 lanes contribute (v, aux); afterwards every lane can see everybody's contribution.
+inline void rendezvous(int op, uint64_t v, uint32_t aux, const uint64_t** vals, const uint32_t** auxs) {
+  Warp* w = W();
+  const int me = w->cur;
+  w->slot[me] = v;
+  w->aux[me] = aux;
+  w->op[me] = op;
+  const uint64_t mygen = w->gen;
+  if (++w->arrived == 32) {
+    for (int i = 0; i < 32; ++i) {
+      if (w->op[i] != op) {
+        fprintf(stderr, "warp_emul: lanes disagree on the collective (lane %d op %d vs lane %d op %d)\n", i, w->op[i], me, op);
+        abort();
+      }
+      w->result[mygen & 1][i] = w->slot[i];
+      w->result_aux[mygen & 1][i] = w->aux[i];
+    }
+    w->arrived = 0;
+    w->collectives++;
+    w->gen++;
+  } else {
+    while (w->gen == mygen) yield_to_sched();
+  }
+  *vals = w->result[mygen & 1];
+  *auxs = w->result_aux[mygen & 1];
+}
+
+inline void check_mask(unsigned mask) {
+  if (mask != 0xffffffffu) {
+    fprintf(stderr, "warp_emul: only full-mask collectives are supported (got %08x)\n", mask);
+    abort();
+  }
+}
+
+inline void fiber_entry() {
+  Warp* w = W();
+  w->body();
+  w->done[w->cur] = true;
+  swapcontext(&w->ctx[w->cur], &w->sched);
+}
+
+// Runs body() once per lane (32 fibers) to completion. Returns number of collectives executed.
+inline uint64_t run_warp(const std::function<void()>& body) {
+  Warp* w = new Warp();
+  Warp* saved = W();
+  W() = w;
+  w->body = body;
+  const size_t kStack = 256 * 1024;
+  for (int i = 0; i < 32; ++i) {
+    w->stack[i] = (char*)malloc(kStack);
+    w->done[i] = false;
+    getcontext(&w->ctx[i]);
+    w->ctx[i].uc_stack.ss_sp = w->stack[i];
+    w->ctx[i].uc_stack.ss_size = kStack;
+    w->ctx[i].uc_link = &w->sched;
+    makecontext(&w->ctx[i], (void (*)())fiber_entry, 0);
+  }
+  int remaining = 32;
+  uint64_t last_gen = ~0ull;
+  int idle_sweeps = 0;
+  while (remaining > 0) {
+    const uint64_t gen_before = w->gen;
+    int ran = 0;
+    for (int i = 0; i < 32; ++i) {
+      if (w->done[i]) continue;
+      w->cur = i;
+      swapcontext(&w->sched, &w->ctx[i]);
+      ++ran;
+      if (w->done[i]) --remaining;
+    }
+    if (w->gen == gen_before && remaining > 0) {
+      // nobody completed a collective in a full sweep: either some lanes exited while others wait,
+      // or lanes are parked at different collectives -> deadlock in real hardware terms.
+      if (++idle_sweeps > 2) {
+        fprintf(stderr, "warp_emul: deadlock (%d lanes alive, %d arrived at a collective)\n", remaining, w->arrived);
+        abort();
+      }
+    } else {
+      idle_sweeps = 0;
+    }
+    (void)last_gen;
+    (void)ran;
+  }
+  const uint64_t n = w->collectives;
+  for (int i = 0; i < 32; ++i) free(w->stack[i]);
+  delete w;
+  W() = saved;
+  return n;
+}
+
+}  // namespace wemu
+
+// ---------------------------------------------------------------- CUDA intrinsics used by the kernels
+template <typename T>
+inline T __shfl_sync(unsigned mask, T v, int src) {
+  wemu::check_mask(mask);
+  static_assert(sizeof(T) <= 8, "shfl value too wide");
+  uint64_t raw = 0;
+  memcpy(&raw, &v, sizeof(T));
+  const uint64_t* vals;
+  const uint32_t* auxs;
+  wemu::rendezvous(wemu::OP_SHFL, raw, 0, &vals, &auxs);
+  T out;
+  memcpy(&out, &vals[src & 31], sizeof(T));
+  return out;
+}
+template <typename T>
+inline T __shfl_up_sync(unsigned mask, T v, unsigned delta) {
+  wemu::check_mask(mask);
+  uint64_t raw = 0;
+  memcpy(&raw, &v, sizeof(T));
+  const uint64_t* vals;
+  const uint32_t* auxs;
+  wemu::rendezvous(wemu::OP_SHFL_UP, raw, 0, &vals, &auxs);
+  const int me = wemu::lane();
+  const int src = me - (int)delta;
+  T out;
+  memcpy(&out, &vals[src < 0 ? me : src], sizeof(T));
+  return out;
+}
+template <typename T>
+inline T __shfl_down_sync(unsigned mask, T v, unsigned delta) {
+  wemu::check_mask(mask);
+  uint64_t raw = 0;
+  memcpy(&raw, &v, sizeof(T));
+  const uint64_t* vals;
+  const uint32_t* auxs;
+  wemu::rendezvous(wemu::OP_SHFL_DOWN, raw, 0, &vals, &auxs);
+  const int me = wemu::lane();
+  const int src = me + (int)delta;
+  T out;
+  memcpy(&out, &vals[src > 31 ? me : src], sizeof(T));
+  return out;
+}
+template <typename T>
+inline T __shfl_xor_sync(unsigned mask, T v, int lanemask) {
+  wemu::check_mask(mask);
+  uint64_t raw = 0;
+  memcpy(&raw, &v, sizeof(T));
+  const uint64_t* vals;
+  const uint32_t* auxs;
+  wemu::rendezvous(wemu::OP_SHFL_XOR, raw, 0, &vals, &auxs);
+  T out;
+  memcpy(&out, &vals[(wemu::lane() ^ lanemask) & 31], sizeof(T));
+  return out;
+}
+inline unsigned __ballot_sync(unsigned mask, int pred) {
+  wemu::check_mask(mask);
+  const uint64_t* vals;
+  const uint32_t* auxs;
+  wemu::rendezvous(wemu::OP_BALLOT, pred ? 1 : 0, 0, &vals, &auxs);
+  unsigned r = 0;
+  for (int i = 0; i < 32; ++i) r |= (unsigned)(vals[i] & 1) << i;
+  return r;
+}
+inline int __any_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) != 0; }
+inline int __all_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) == 0xffffffffu; }
+inline void __syncwarp(unsigned mask = 0xffffffffu) {
+  wemu::check_mask(mask);
+  const uint64_t* vals;
+  const uint32_t* auxs;
+  wemu::rendezvous(wemu::OP_SYNC, 0, 0, &vals, &auxs);
+}
+inline unsigned __match_any_sync(unsigned mask, unsigned v) {
+  wemu::check_mask(mask);
+  const uint64_t* vals;
+  const uint32_t* auxs;
+  wemu::rendezvous(wemu::OP_MATCH, v, 0, &vals, &auxs);
+  unsigned r = 0;
+  for (int i = 0; i < 32; ++i) r |= (unsigned)(vals[i] == (uint64_t)v) << i;
+  return r;
+}
+inline unsigned __reduce_add_sync(unsigned mask, unsigned v) {
+  wemu::check_mask(mask);
+  const uint64_t* vals;
+  const uint32_t* auxs;
+  wemu::rendezvous(wemu::OP_REDUCE, v, 1, &vals, &auxs);
+  unsigned r = 0;
+  for (int i = 0; i < 32; ++i) r += (unsigned)vals[i];
+  return r;
+}
+inline unsigned __reduce_max_sync(unsigned mask, unsigned v) {
+  wemu::check_mask(mask);
+  const uint64_t* vals;
+  const uint32_t* auxs;
+  wemu::rendezvous(wemu::OP_REDUCE, v, 2, &vals, &auxs);
+  unsigned r = 0;
+  for (int i = 0; i < 32; ++i) r = (unsigned)vals[i] > r ? (unsigned)vals[i] : r;
+  return r;
+}
+inline unsigned __reduce_min_sync(unsigned mask, unsigned v) {
+  wemu::check_mask(mask);
+  const uint64_t* vals;
+  const uint32_t* auxs;
+  wemu::rendezvous(wemu::OP_REDUCE, v, 3, &vals, &auxs);
+  unsigned r = 0xffffffffu;
+  for (int i = 0; i < 32; ++i) r = (unsigned)vals[i] < r ? (unsigned)vals[i] : r;
+  return r;
+}
+inline unsigned __reduce_or_sync(unsigned mask, unsigned v) {
+  wemu::check_mask(mask);
+  const uint64_t* vals;
+  const uint32_t* auxs;
+  wemu::rendezvous(wemu::OP_REDUCE, v, 4, &vals, &auxs);
+  unsigned r = 0;
+  for (int i = 0; i < 32; ++i) r |= (unsigned)vals[i];
+  return r;
+}
+inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
+inline int __ffs(int v) { return __builtin_ffs(v); }
+inline unsigned __brev(unsigned v) {
+  unsigned r = 0;
+  for (int i = 0; i < 32; ++i) r |= ((v >> i) & 1u) << (31 - i);
+  return r;
+}
+inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned shift) {
+  const uint64_t w = ((uint64_t)hi << 32) | lo;
+  return (unsigned)(w >> (shift & 31));
+}
+inline unsigned __funnelshift_l(unsigned lo, unsigned hi, unsigned shift) {
+  const uint64_t w = ((uint64_t)hi << 32) | lo;
+  return (unsigned)((w << (shift & 31)) >> 32);
+}
+template <typename T>
+inline T atomicAdd(T* p, T v) { T old = *p; *p = old + v; return old; }
+template <typename T>
+inline T atomicOr(T* p, T v) { T old = *p; *p = old | v; return old; }
+template <typename T>
+inline T atomicMax(T* p, T v) { T old = *p; if (v > old) *p = v; return old; }
+struct uint4 { unsigned x, y, z, w; };
+struct uint2 { unsigned x, y; };
