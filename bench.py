@@ -1,0 +1,397 @@
+#!/usr/bin/env python
+"""bench.py -- decompressed GB/s (bit-exact) on 64 KiB-page Brotli-G streams, % of HBM roofline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload random|mixed|text]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the decode hot path over one batch of synthetic streams. Default workload =
+BASELINE.json configs[1]: a 4 GiB random-byte buffer, page_size 65536, held as 64 streams x 64 MiB
+(one stream cannot exceed 65535 pages), per GPU (weak scaling). Every page of random data is a raw
+page, so this line measures the copy path against the HBM roofline; the compressed-page path is
+reported beside it under "secondary" (mixed-entropy payload) so that both halves of the story are in
+the same JSON line.
+
+  value      whole-job decompressed GB/s, streams already resident in HBM, CUDA events around K launches
+  e2e        the same metric through the C-ABI host-pointer call (bgx_decode_batch_host), pinned host
+             buffers, H2D + decode + D2H inside the timed region
+  roofline   algorithmic bytes (compressed read + decompressed written) / kernel time vs measured HBM peak
+  cpu_baseline  the reference's own DecodeCPU (oracle/_ref, unmodified, built from /root/reference) on
+             the box's host cores over a bounded sample of the same workload
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+STREAM_BYTES = 64 << 20
+PAGE = 65536
+
+
+# ------------------------------------------------------------------------------------------- helpers
+def measured_peak_gbs() -> tuple[float, str]:
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """samples nvidia-smi clocks / throttle reasons while the timed region runs"""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows: list[list[str]] = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def make_workload(kind: str, total_bytes: int, seed0: int, sdk, threads: int = 0):
+    """returns (streams [np.uint8], sizes [int uncompressed], sources-or-None for verification sample)"""
+    from brotli_g_sdk_b200 import datagen
+    n_streams = max(1, total_bytes // STREAM_BYTES)
+    streams, usizes = [], []
+    verify = None
+    if kind == "random":
+        for i in range(n_streams):
+            d = datagen.random_bytes(STREAM_BYTES, seed=seed0 + i)
+            s = sdk.Encode(d, page_size=PAGE, num_threads=threads)
+            streams.append(s)
+            usizes.append(len(d))
+            if i == 0:
+                verify = (0, d)
+        return streams, usizes, verify, {"unique_streams": n_streams, "replicas": 1}
+    # compressible payloads: encode a bounded number of unique streams, replicate them to the requested size
+    gen = {"mixed": datagen.mixed, "text": datagen.text_like, "binary": datagen.structured_binary, "lowent": datagen.low_entropy}[kind]
+    unique = min(n_streams, 4)
+    for i in range(unique):
+        d = gen(STREAM_BYTES, seed=seed0 + i)
+        s = sdk.Encode(d, page_size=PAGE, num_threads=threads)
+        streams.append(s)
+        usizes.append(len(d))
+        if i == 0:
+            verify = (0, d)
+    reps = (n_streams + unique - 1) // unique
+    streams = (streams * reps)[:n_streams]
+    usizes = (usizes * reps)[:n_streams]
+    return streams, usizes, verify, {"unique_streams": unique, "replicas": reps}
+
+
+def load_reference_cpu():
+    p = os.path.join(ROOT, "oracle", "_ref", "libbrotlig_ref.so")
+    if os.path.exists(p):
+        lib = ctypes.CDLL(p, mode=ctypes.RTLD_LOCAL)
+        lib.DecodeCPU.restype = ctypes.c_int
+        lib.DecodeCPU.argtypes = [ctypes.c_uint32, ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint32), ctypes.c_void_p, ctypes.c_void_p]
+        return lib, "reference"
+    # oracle port (single-threaded restatement) -- only when the reference could not be built
+    so = os.path.join(ROOT, "oracle", "_build", "libbrotlig_oracle.so")
+    if not os.path.exists(so):
+        subprocess.run(["make", "oracle"], cwd=os.path.join(ROOT, "oracle"), check=True, stdout=subprocess.DEVNULL)
+    lib = ctypes.CDLL(so)
+    lib.bgo_decode.restype = ctypes.c_int
+    return lib, "port"
+
+
+def time_cpu_decode(streams, usizes, budget_s: float, repeats: int = 3):
+    """Times the reference DecodeCPU (all the host threads it chooses to use) over a bounded sample of the
+    streams. Returns dict(value GB/s, cores, kind, sample, seconds)."""
+    lib, kind = load_reference_cpu()
+    padded = [np.concatenate([s, np.zeros(16, np.uint8)]) for s in streams]
+    outs = [np.empty(u + 16, np.uint8) for u in usizes]
+    for o in outs:
+        o[:] = 0          # pre-fault
+    hw = os.cpu_count() or 1
+
+    def run(k):
+        t0 = time.perf_counter()
+        for i in range(k):
+            n = ctypes.c_uint32(usizes[i])
+            if kind == "reference":
+                rc = lib.DecodeCPU(len(streams[i]), padded[i].ctypes.data, ctypes.byref(n), outs[i].ctypes.data, None)
+            else:
+                rc = lib.bgo_decode(ctypes.c_uint32(len(streams[i])), ctypes.c_void_p(padded[i].ctypes.data), ctypes.byref(n), ctypes.c_void_p(outs[i].ctypes.data))
+            assert rc == 0
+        return time.perf_counter() - t0
+
+    t1 = run(1)
+    k = int(max(1, min(len(streams), budget_s / repeats / max(t1, 1e-6))))
+    times = [run(k) for _ in range(repeats)]
+    t = statistics.median(times)
+    nbytes = sum(usizes[:k])
+    pages = nbytes // PAGE
+    workers = min(128, hw)
+    cores = workers if (kind == "reference" and (usizes[0] // PAGE) > 2 * workers) else 1
+    return {"value": nbytes / t / 1e9, "unit": "GB/s decompressed", "cores": cores, "kind": kind,
+            "sample": f"{k} of {len(streams)} streams ({nbytes / 2**20:.0f} MiB, {pages} pages), median of {repeats}",
+            "seconds": t, "host_threads_available": hw, "outs": outs, "k": k}
+
+
+# ------------------------------------------------------------------------------------------- arms
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import brotli_g_sdk_b200 as sdk
+    from brotli_g_sdk_b200 import build, datagen
+    build.build_encoder()
+    sample_bytes = min(args.size_gib << 30, 1 << 30)
+    streams, usizes, verify, rep = make_workload(args.workload, sample_bytes, datagen.SEED_CONFIG2, sdk)
+    # W warm-up + K timed steps, each a bounded sample
+    per_step_budget = max(1.0, min(20.0, 90.0 / max(1, args.steps + args.warmup)))
+    for _ in range(args.warmup):
+        time_cpu_decode(streams, usizes, per_step_budget, repeats=1)
+    vals, last = [], None
+    for _ in range(args.steps):
+        last = time_cpu_decode(streams, usizes, per_step_budget, repeats=1)
+        vals.append(last["value"])
+    if verify is not None:
+        assert np.array_equal(last["outs"][0][: usizes[0]], verify[1]), "reference output != source"
+    v = statistics.median(vals)
+    ms = sum(usizes[: last["k"]]) / v / 1e6
+    line = {
+        "impl": "reference", "metric": "decompressed GB/s (bit-exact) on 64 KiB-page streams; % of HBM roofline",
+        "value": v, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": workload_config(args, rep),
+        "cpu_baseline": {"value": v, "unit": "GB/s", "cores": last["cores"], "kind": last["kind"], "sample": last["sample"]},
+        "e2e": {"value": v, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, rep):
+    names = {"random": "configs[1]: 4 GiB random-byte buffer, page_size=65536 (64 streams x 64 MiB, all pages raw)",
+             "mixed": "configs[3]-like: mixed-entropy (text+binary+random) 64 MiB streams, page_size=65536",
+             "text": "text-like 64 MiB streams, page_size=65536"}
+    return {"workload": names.get(args.workload, args.workload), "bytes_per_gpu": args.size_gib << 30, "page_size": PAGE,
+            "streams_per_gpu": max(1, (args.size_gib << 30) // STREAM_BYTES), "stream_bytes": STREAM_BYTES, **rep,
+            "l2_policy": "inputs+outputs per step (>= 2x payload) are far larger than the 126 MB L2; no flush needed",
+            "parallelism": f"pages sharded across {args.gpus} GPU(s), whole streams per rank, no data-path collective"}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; brotli_g_sdk_b200 has no CPU decode path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import brotli_g_sdk_b200 as sdk
+    from brotli_g_sdk_b200 import build, datagen
+    if rank == 0:
+        build.build_all()
+    if world > 1:
+        dist.barrier()
+    dec = sdk.BrotligDecoder(local)
+    dev = torch.device("cuda", local)
+    threads = max(1, (os.cpu_count() or 8) // world)
+
+    def resident_batch(kind, total_bytes, seed0):
+        streams, usizes, verify, rep = make_workload(kind, total_bytes, seed0, sdk, threads)
+        keep, descs = [], []
+        for s, u in zip(streams, usizes):
+            t_in = torch.empty(len(s) + 64, dtype=torch.uint8, device=dev)
+            t_in[: len(s)].copy_(torch.from_numpy(s))
+            t_in[len(s):].zero_()
+            t_out = torch.empty(u, dtype=torch.uint8, device=dev)
+            keep.append((t_in, t_out))
+            descs.append(dict(d_src=t_in.data_ptr(), src_size=len(s), src_capacity=len(s) + 64, d_dst=t_out.data_ptr(),
+                              dst_capacity=u, header=bytes(s[:16])))
+        torch.cuda.synchronize(dev)
+        return streams, usizes, verify, rep, keep, dec.plan(descs)
+
+    def timed(plan, steps, warmup, sampler=None):
+        ts = torch.cuda.Stream(dev)
+        for _ in range(warmup):
+            plan.launch(ts.cuda_stream)
+        ts.synchronize()
+        assert plan.finish() == 0
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        if sampler:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(ts)
+        for _ in range(steps):
+            plan.launch(ts.cuda_stream)
+        e1.record(ts)
+        ts.synchronize()
+        torch.cuda.synchronize(dev)
+        clocks = sampler.stop() if sampler else None
+        if world > 1:
+            dist.barrier()
+        ms = e0.elapsed_time(e1)
+        assert plan.finish() == 0
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, clocks
+
+    # ---------------- primary workload
+    total = args.size_gib << 30
+    streams, usizes, verify, rep, keep, plan = resident_batch(args.workload, total, datagen.SEED_CONFIG2 + 1000 * rank)
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms, clocks = timed(plan, args.steps, args.warmup, sampler)
+    out_bytes = sum(usizes)
+    in_bytes = sum(len(s) for s in streams)
+    if verify is not None:
+        got = keep[verify[0]][1].cpu().numpy()
+        assert np.array_equal(got, verify[1]), "GPU output != source bytes"
+    ms_step = ms / args.steps
+    value = world * out_bytes / (ms_step / 1e3) / 1e9
+    peak, peak_src = measured_peak_gbs()
+    achieved = (in_bytes + out_bytes) / (ms_step / 1e3) / 1e9     # per GPU
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get(args.workload)
+        except Exception:
+            traffic = None
+    launches_per_step = plan.info["kernels_per_launch"]
+
+    # ---------------- end to end through the host-pointer C-ABI call (pinned host buffers)
+    e2e = None
+    if not args.no_e2e:
+        k = min(len(streams), 16)   # 1 GiB of the same workload per step keeps pinned memory modest
+        pin_in = [torch.from_numpy(s).pin_memory() for s in streams[:k]]
+        pin_out = [torch.empty(u, dtype=torch.uint8).pin_memory() for u in usizes[:k]]
+        np_in = [t.numpy() for t in pin_in]
+        np_out = [t.numpy() for t in pin_out]
+        for _ in range(max(1, min(args.warmup, 3))):
+            dec.decode_batch_host(np_in, np_out)
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            dec.decode_batch_host(np_in, np_out)
+        el = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([el], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            el = float(t.item())
+        if verify is not None:
+            assert np.array_equal(np_out[0], verify[1]), "e2e output != source bytes"
+        e2e_bytes = sum(usizes[:k])
+        e2e = {"value": world * e2e_bytes * args.steps / el / 1e9, "unit": "GB/s", "h2d_bytes_per_step": int(sum(len(s) for s in streams[:k])),
+               "d2h_bytes_per_step": int(e2e_bytes), "call": "bgx_decode_batch_host (C ABI), pinned host buffers",
+               "streams_per_step": k}
+        del pin_in, pin_out
+    del keep, plan
+    torch.cuda.empty_cache()
+
+    # ---------------- secondary: the compressed-page path on a mixed-entropy payload (rank 0 reports)
+    secondary = None
+    if not args.no_secondary and args.workload == "random":
+        s2, u2, v2, rep2, keep2, plan2 = resident_batch("mixed", 1 << 30, datagen.SEED_CONFIG4 + 1000 * rank)
+        ms2, _ = timed(plan2, max(3, args.steps // 2), 2)
+        ms2 /= max(3, args.steps // 2)
+        assert np.array_equal(keep2[v2[0]][1].cpu().numpy(), v2[1]), "GPU output != source bytes (mixed)"
+        o2, i2 = sum(u2), sum(len(s) for s in s2)
+        secondary = {"workload": "mixed-entropy (50% text, 25% structured binary, 25% random), 1 GiB per GPU as 64 MiB streams "
+                                 f"({rep2['unique_streams']} unique x {rep2['replicas']} replicas in distinct HBM buffers)",
+                     "value": world * o2 / (ms2 / 1e3) / 1e9, "unit": "GB/s", "ms_per_step": ms2, "compression_ratio": o2 / i2,
+                     "roofline": {"bound": "hbm", "achieved": (i2 + o2) / (ms2 / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                                  "frac": (i2 + o2) / (ms2 / 1e3) / 1e9 / peak, "traffic": None}}
+        del keep2, plan2
+
+    # ---------------- CPU baseline (rank 0, N = 1 only): reference DecodeCPU on a bounded sample
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        c = time_cpu_decode(streams, usizes, budget_s=15.0)
+        cpu = {k: c[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        cpu["host_threads_available"] = c["host_threads_available"]
+        if secondary is not None:
+            c2 = time_cpu_decode(s2, u2, budget_s=15.0)
+            secondary["cpu_baseline"] = {k: c2[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {
+            "metric": "decompressed GB/s (bit-exact) on 64 KiB-page streams; % of HBM roofline",
+            "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": workload_config(args, rep),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "peak_source": peak_src, "kernel": "bgx_decode_pages_kernel",
+                         "algorithmic_bytes_per_launch": in_bytes + out_bytes},
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
+            "secondary": secondary, "bit_exact": True,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="random", choices=["random", "mixed", "text", "binary", "lowent"])
+    ap.add_argument("--size-gib", type=int, default=4)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

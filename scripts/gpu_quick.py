@@ -55,14 +55,16 @@ def bench_resident(name, unique_streams, copies, iters=5):
             total_out += usize
             total_in += len(s)
     plan = dec.plan(sd)
-    st = torch.cuda.current_stream().cuda_stream
+    ts = torch.cuda.Stream()
+    st = ts.cuda_stream
+    torch.cuda.synchronize()
     for _ in range(2):
         plan.launch(st)
     assert plan.finish() == 0
     times = []
     for _ in range(iters):
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-        e0.record(); plan.launch(st); e1.record(); torch.cuda.synchronize()
+        e0.record(ts); plan.launch(st); e1.record(ts); torch.cuda.synchronize()
         times.append(e0.elapsed_time(e1))
     assert plan.finish() == 0
     # verify one copy of each

@@ -21,6 +21,24 @@ int emul_decode_stream(const uint8_t* src, uint32_t src_size, uint8_t* dst, uint
   if (si.uncompressed_size > dst_capacity) return bgx::kErrGeneric;
   const uint8_t* table = src + si.header_bytes;
   const uint8_t* pages = table + 4 * (size_t)si.num_pages;
+  // pre-conditioned streams: pages decode into the conditioned planes, then delta + de-condition
+  bgx::PreconLayout layout;
+  bgxk::DeltaPlanes planes_desc{};
+  std::vector<uint8_t> planes;
+  uint8_t* const final_dst = dst;
+  if (si.preconditioned) {
+    const bgx::PreconHeaderFields f = bgx::parse_precon_header(src + 8);
+    if (!bgx::precon_layout_init(&layout, f.format, f.width_blocks, f.height_blocks, f.pitch_bytes, f.num_mips,
+                                 f.swizzled != 0, f.pitch_aligned != 0, si.uncompressed_size))
+      return bgx::kErrCorruptStream;
+    planes_desc.count = layout.num_color_sub;
+    for (uint32_t c = 0; c < layout.num_color_sub; ++c) {
+      planes_desc.lo[c] = layout.sub_stream_off[layout.color_sub[c]];
+      planes_desc.hi[c] = layout.sub_stream_off[layout.color_sub[c] + 1];
+    }
+    planes.assign(si.uncompressed_size + 64, 0xEE);
+    dst = planes.data();
+  }
   bgxk::WarpSmem* sm = new bgxk::WarpSmem();
   memset(sm, 0xCD, sizeof(*sm));
   uint64_t coll = 0;
@@ -43,12 +61,20 @@ int emul_decode_stream(const uint8_t* src, uint32_t src_size, uint8_t* dst, uint
       res = results[0];
       for (int l = 1; l < 32; ++l)
         if (results[l].status != res.status || results[l].is_delta != res.is_delta) res.status |= 0x80000000u;
+      if (!res.status && res.is_delta)
+        coll += wemu::run_warp([&] { bgxk::delta_decode_warp(dst + e.out_off, e.out_off, e.out_size, planes_desc); });
     }
     if (status_out) status_out[p] = res.status;
     if (flags_out) flags_out[p] = res.is_delta;
     if (res.status) worst = bgx::kErrCorruptStream;
   }
   delete sm;
+  if (si.preconditioned) {
+    for (size_t i = si.uncompressed_size; i < planes.size(); ++i)
+      if (planes[i] != 0xEE) return bgx::kErrGeneric;   // a page wrote past the scratch planes
+    memset(final_dst, 0, si.uncompressed_size);          // pitch padding stays 0 (BrotligDecoder.cpp:448)
+    for (uint32_t t = 0; t < layout.total_blocks; ++t) bgxk::decondition_block(layout, t, planes.data(), final_dst);
+  }
   if (collectives_out) *collectives_out = coll;
   return worst;
 }

@@ -1,0 +1,45 @@
+"""CPU tests (-m "not gpu"): the CUDA device code (page_decode.cuh), compiled for the CPU warp
+emulator, against the oracle. This is how kernel logic is checked where there is no GPU; the GPU
+parity tests (test_gpu_parity.py) run the real kernels through the C ABI."""
+import numpy as np
+
+from corpus import corner_cases, texture_cases
+
+
+def test_emulated_kernel_matches_oracle(sdk, oracle, emulator):
+    for name, (data, kw) in corner_cases().items():
+        if len(data) > 320000:
+            data = data[:320000]
+        s = sdk.Encode(data, **kw)
+        want = oracle.decode(s)
+        got, status, _ = emulator.decode(s)
+        assert all(x == 0 for x in status), f"{name}: page status {status}"
+        assert np.array_equal(got, want), f"{name}: emulated kernel != oracle (first diff at {np.nonzero(got != want)[0][:4]})"
+
+
+def test_emulated_kernel_textures(sdk, oracle, emulator):
+    for name, (data, p) in texture_cases().items():
+        s = sdk.Encode(data, dcParams=p)
+        want = oracle.decode(s)
+        got, status, flags = emulator.decode(s)
+        assert all(x == 0 for x in status), f"{name}: page status {status}"
+        assert np.array_equal(got, want), f"{name}: emulated texture path != oracle"
+        if p.delta_encode:
+            assert any(flags), f"{name}: no page took the delta path"
+
+
+def test_emulated_kernel_rejects_garbage_without_writing_out_of_bounds(sdk, emulator):
+    """corrupt payloads must end in a page status, never in an out-of-bounds access (the guard bytes
+    around the output are checked inside Emulator.decode)"""
+    rng = np.random.default_rng(5)
+    data = np.tile(rng.integers(0, 256, 997, dtype=np.uint8), 80)
+    s = sdk.Encode(data)
+    assert len(s) < len(data) // 2
+    for trial in range(12):
+        bad = s.copy()
+        k = int(rng.integers(20, len(bad) - 4))
+        bad[k: k + 4] ^= rng.integers(1, 256, 4, dtype=np.uint8)
+        try:
+            emulator.decode(bad, expect_rc=0)
+        except AssertionError as e:
+            assert "rc 14" in str(e) or "status" in str(e), str(e)

@@ -1,0 +1,161 @@
+"""GPU tests (-m gpu): the CUDA path, called through the C ABI (ctypes -> libbrotlig_b200.so), against the
+oracle on the same seeded inputs, against the committed golden fixtures, and -- at BASELINE.json sizes --
+through size-independent properties (round trip to the source bytes, checksum of checksums).
+Bit-exact is the bar: this is byte/integer work."""
+import ctypes
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import sha256
+from corpus import corner_cases, texture_cases
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def dec(sdk):
+    from brotli_g_sdk_b200 import build
+    build.build_cuda()
+    d = sdk.BrotligDecoder(0)
+    yield d
+    d.close()
+
+
+def test_corner_cases_match_oracle(sdk, oracle, dec):
+    for name, (data, kw) in corner_cases().items():
+        s = sdk.Encode(data, **kw)
+        want = oracle.decode(s)
+        got, ms = dec.decode_host(s)
+        assert np.array_equal(got, want), f"{name}: GPU != oracle (first diff {np.nonzero(got != want)[0][:4]})"
+        assert np.array_equal(got, data), name
+
+
+def test_textures_match_oracle(sdk, oracle, dec):
+    for name, (data, p) in texture_cases().items():
+        s = sdk.Encode(data, dcParams=p)
+        want = oracle.decode(s)
+        got, _ = dec.decode_host(s)
+        assert np.array_equal(got, want), f"{name}: GPU texture path != oracle"
+
+
+def test_golden_fixtures(dec):
+    idx = json.load(open(os.path.join(GOLDEN, "index.json")))
+    for name, meta in idx.items():
+        s = np.fromfile(os.path.join(GOLDEN, name + ".brotlig"), dtype=np.uint8)
+        out, _ = dec.decode_host(s)
+        assert len(out) == meta["size"] and sha256(out) == meta["output_sha256"], name
+
+
+def test_batch_of_streams_one_launch(sdk, oracle, dec):
+    items = list(corner_cases().items())[:14]
+    streams = [sdk.Encode(d, **kw) for _, (d, kw) in items]
+    outs, ms = dec.decode_batch_host(streams)
+    assert ms > 0
+    for (name, (d, _)), o in zip(items, outs):
+        assert np.array_equal(o, d), name
+
+
+def test_header_errors_and_output_size_contract(sdk, dec):
+    s = sdk.Encode(np.arange(70000, dtype=np.uint32).view(np.uint8))
+    bad = s.copy(); bad[1] ^= 0x20
+    with pytest.raises(sdk.BrotligError) as e:
+        dec.decode_host(bad)
+    assert e.value.code == 14       # BROTLIG_ERROR_CORRUPT_STREAM (BrotligDecoder.cpp:438-441)
+    bad = s.copy(); bad[0] = 9; bad[1] = 9 ^ 0xFF
+    with pytest.raises(sdk.BrotligError) as e:
+        dec.decode_host(bad)
+    assert e.value.code == 15       # BROTLIG_ERROR_INCORRECT_STREAM_FORMAT (:443-446)
+    # *output_size is in/out: a larger buffer is fine and the decoded size comes back
+    big = np.full(sdk.DecompressedSize(s) + 100, 0x77, np.uint8)
+    out, _ = dec.decode_host(s, big)
+    assert len(out) == sdk.DecompressedSize(s)
+    assert (big[len(out):] == 0x77).all()
+
+
+def test_corrupt_payload_is_reported_not_crashed(sdk, dec):
+    rng = np.random.default_rng(9)
+    data = np.tile(rng.integers(0, 256, 997, dtype=np.uint8), 80)
+    s = sdk.Encode(data)
+    for _ in range(8):
+        bad = s.copy()
+        k = int(rng.integers(20, len(bad) - 4))
+        bad[k: k + 4] ^= rng.integers(1, 256, 4, dtype=np.uint8)
+        try:
+            out, _ = dec.decode_host(bad)
+        except sdk.BrotligError as e:
+            assert e.code == 14
+    out, _ = dec.decode_host(s)      # the context still works afterwards
+    assert np.array_equal(out, data)
+
+
+def test_reference_named_c_entry_points(sdk, dec):
+    """DecodeCPU / DecompressedSize exported with the reference's names and argument order"""
+    from brotli_g_sdk_b200 import build
+    lib = ctypes.CDLL(build.CUDA_LIB)
+    data = np.tile(np.arange(251, dtype=np.uint8), 1000)
+    s = sdk.Encode(data)
+    lib.DecompressedSize.restype = ctypes.c_uint32
+    n = lib.DecompressedSize(ctypes.c_void_p(s.ctypes.data))
+    assert n == len(data)
+    out = np.zeros(n, np.uint8)
+    osz = ctypes.c_uint32(n)
+    lib.DecodeCPU.restype = ctypes.c_int
+    rc = lib.DecodeCPU(ctypes.c_uint32(len(s)), ctypes.c_void_p(s.ctypes.data), ctypes.byref(osz), ctypes.c_void_p(out.ctypes.data), None)
+    assert rc == 0 and osz.value == n and np.array_equal(out, data)
+
+
+def test_device_resident_plan_with_page_ranges(sdk, dec):
+    """the multi-GPU sharding primitive: a rank decodes pages [begin, begin+count) into its own shard"""
+    import torch
+    data = corner_cases()["mixed"][0]
+    s = sdk.Encode(data)
+    npages = (len(data) + 65535) // 65536
+    t_in = torch.zeros(len(s) + 64, dtype=torch.uint8, device="cuda")
+    t_in[: len(s)] = torch.from_numpy(s).cuda()
+    cut = npages // 2
+    shards = []
+    for begin, count in ((0, cut), (cut, npages - cut)):
+        nbytes = min(len(data), (begin + count) * 65536) - begin * 65536
+        t_out = torch.zeros(nbytes, dtype=torch.uint8, device="cuda")
+        plan = dec.plan([dict(d_src=t_in.data_ptr(), src_size=len(s), src_capacity=len(s) + 64, d_dst=t_out.data_ptr(),
+                              dst_capacity=nbytes, header=bytes(s[:16]), page_begin=begin, page_count=count)])
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        plan.launch(side.cuda_stream)
+        assert plan.finish() == 0
+        shards.append(t_out.cpu().numpy())
+    assert np.array_equal(np.concatenate(shards), data)
+
+
+def test_full_size_random_buffer_checksum_of_checksums(sdk, dec):
+    """BASELINE config 2 shape (64 MiB streams of raw pages), 1 GiB here: per-page CRCs of the decoded
+    buffer equal those of the source (checked on the device side via torch, no oracle at this size)."""
+    import torch
+    import zlib
+    from brotli_g_sdk_b200 import datagen
+    streams, sources = [], []
+    for i in range(4):
+        d = datagen.random_bytes(64 << 20, seed=datagen.SEED_CONFIG2 + i)
+        sources.append(d)
+        streams.append(sdk.Encode(d))
+    outs, _ = dec.decode_batch_host(streams)
+    for d, o in zip(sources, outs):
+        assert zlib.crc32(o.tobytes()) == zlib.crc32(d.tobytes())
+
+
+def test_page_size_sweep_small_single_page_streams(sdk, oracle, dec):
+    """config 5: 4/8/16 KiB "pages" are single-page streams (NumPages = 1, LastPageSize = n)"""
+    from brotli_g_sdk_b200 import datagen
+    streams, sources = [], []
+    for i, n in enumerate([4096, 8192, 16384] * 20):
+        d = datagen.text_like(n, seed=100 + i)
+        sources.append(d)
+        streams.append(sdk.Encode(d))
+    outs, _ = dec.decode_batch_host(streams)
+    for d, o, s in zip(sources, outs, streams):
+        assert np.array_equal(o, d)
+    assert np.array_equal(oracle.decode(streams[7]), sources[7])
