@@ -51,43 +51,66 @@ def measured_peak_gbs() -> tuple[float, str]:
 
 
 class ClockSampler:
-    """samples nvidia-smi clocks / throttle reasons while the timed region runs"""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """samples SM clock / throttle reasons through NVML (a few hundred Hz) while the timed region runs;
+    falls back to polling nvidia-smi when pynvml is unavailable"""
 
     def __init__(self, index: int):
         self.index = index
-        self.rows: list[list[str]] = []
-        self.proc = None
+        self.samples: list[tuple[float, int]] = []
+        self.max_mhz = None
+        self.power = []
+        self._stop = threading.Event()
+        self._t = None
+        self._nvml = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
+            import pynvml
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
         except Exception:
-            self.proc = None
+            self._nvml = None
+        self._t = threading.Thread(target=self._run_nvml if self._nvml else self._run_smi, daemon=True)
+        self._t.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+    def _run_nvml(self):
+        n = self._nvml
+        while not self._stop.is_set():
+            try:
+                mhz = float(n.nvmlDeviceGetClockInfo(self._h, n.NVML_CLOCK_SM))
+                try:
+                    reasons = int(n.nvmlDeviceGetCurrentClocksEventReasons(self._h))
+                except Exception:
+                    reasons = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self._h))
+                self.samples.append((mhz, reasons))
+                self.power.append(n.nvmlDeviceGetPowerUsage(self._h) / 1000.0)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def _run_smi(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.active"
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=2).stdout.strip().split(",")
+                self.samples.append((float(out[0]), int(out[2].strip(), 16)))
+                self.max_mhz = float(out[1])
+            except Exception:
+                pass
 
     def stop(self) -> dict:
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm)}
+        self._stop.set()
+        if self._t:
+            self._t.join(timeout=3)
+        bits = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+        sm = [m for m, _ in self.samples]
+        reasons = sorted({name for _, r in self.samples for bit, name in bits.items() if r & bit})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                "samples": len(sm), "power_w_max": max(self.power) if self.power else None,
+                "source": "nvml" if self._nvml else "nvidia-smi"}
 
 
 def make_workload(kind: str, total_bytes: int, seed0: int, sdk, threads: int = 0):
@@ -261,6 +284,7 @@ def run_ours(args):
         torch.cuda.synchronize(dev)
         if sampler:
             sampler.start()
+            time.sleep(0.02)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(ts)
         for _ in range(steps):

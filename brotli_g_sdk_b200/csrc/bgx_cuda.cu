@@ -254,8 +254,12 @@ int bgx_plan_create(bgx_context* ctx, const bgx_stream* streams, uint32_t n, bgx
     StreamInfo si;
     const int rc = bgx::parse_stream_header(s.header, &si);
     if (rc) { ctx->err = "stream " + std::to_string(i) + ": bad header"; return rc; }
-    if ((reinterpret_cast<uintptr_t>(s.d_src) & 3u) != 0) { ctx->err = "stream pointer must be 4-byte aligned"; return bgx::kErrGeneric; }
+    if ((reinterpret_cast<uintptr_t>(s.d_src) & 15u) != 0) { ctx->err = "stream pointer must be 16-byte aligned"; return bgx::kErrGeneric; }
     const uint64_t table_end = (uint64_t)si.header_bytes + 4ull * si.num_pages;
+    if (s.src_capacity < ((s.src_size + 15u) & ~15u)) {
+      ctx->err = "src_capacity must cover the stream rounded up to 16 bytes (the input is staged in 16-byte chunks)";
+      return bgx::kErrGeneric;
+    }
     if (table_end > s.src_size || s.src_capacity < s.src_size) { ctx->err = "stream " + std::to_string(i) + ": truncated"; return bgx::kErrCorruptStream; }
     uint32_t begin = s.page_begin, count = s.page_count ? s.page_count : (si.num_pages > begin ? si.num_pages - begin : 0);
     if (begin > si.num_pages || count > si.num_pages - begin) { ctx->err = "page range outside the stream"; return bgx::kErrGeneric; }
@@ -394,7 +398,7 @@ int bgx_decode_batch_host(bgx_context* ctx, uint32_t n, const uint8_t* const* in
     memset(&s, 0, sizeof s);
     s.d_src = ctx->d_in + in_off[i];
     s.src_size = input_sizes[i];
-    s.src_capacity = input_sizes[i];
+    s.src_capacity = (input_sizes[i] + 15u) & ~15u;   // the arena slot has kInputSlackBytes of slack
     s.d_dst = ctx->d_out + out_off[i];
     s.dst_capacity = usize[i];
     memcpy(s.header, inputs[i], std::min<uint32_t>(16, input_sizes[i]));

@@ -33,7 +33,7 @@
 #ifndef BGX_EMULATED
 #include <cuda_runtime.h>
 #define BGX_DEV __device__ __forceinline__
-#define BGX_DEV_NOINLINE __device__ __noinline__
+#define BGX_DEV_NOINLINE __device__ __forceinline__
 #else
 #define BGX_DEV inline
 #define BGX_DEV_NOINLINE inline
@@ -41,12 +41,21 @@
 
 namespace bgxk {
 
+#ifdef BGX_STATS   // emulator-only instrumentation (never defined in the CUDA build)
+struct EmuStats { uint64_t rounds, slow_rounds, wavefronts, sum_max_cpy, copy_bytes, copies, ins_bytes, sum_max_ins, ring_iters,
+                  lits, coop_copies, far_bytes, overlap_copies, dep_copies; };
+inline EmuStats& emu_stats() { static EmuStats s; return s; }
+#define BGX_STAT(expr) do { if (lane == 0) { expr; } } while (0)
+#else
+#define BGX_STAT(expr) do { } while (0)
+#endif
+
 constexpr unsigned kFull = 0xffffffffu;
-constexpr int kCmdLutBits = 10;
+constexpr int kCmdLutBits = 9;
 constexpr int kLitLutBits = 10;
 constexpr int kDistLutBits = 9;
-constexpr uint32_t kLitQ = 1024;      // literal ring bytes (power of two, multiple of 32)
-constexpr uint32_t kRing = 4096;      // output ring bytes (power of two)
+constexpr uint32_t kLitQ = 512;       // literal ring bytes (power of two, multiple of 32)
+constexpr uint32_t kRing = 2048;      // output ring bytes (power of two, >= kFlushChunk + kRoundMax)
 constexpr uint32_t kRoundMax = 1024;  // largest round (bytes produced) the ring path accepts
 constexpr uint32_t kFlushChunk = 512; // 32 lanes x 16 B
 constexpr uint32_t kCoopLen = 32;     // inserts/copies at least this long are done by the whole warp
@@ -72,39 +81,94 @@ struct WarpSmem {
   uint16_t lut_dist[1 << kDistLutBits];
   uint16_t sorted_cmd[bgx::kNumCmdSymbols];
   uint16_t sorted_dist[bgx::kNumDistSymbols];
-  uint16_t sorted_lit[bgx::kNumLitSymbols];
+  uint8_t sorted_lit[bgx::kNumLitSymbols];
   HuffAux aux[3];
   uint32_t lenlut[48];              // [0..23] insert code, [24..47] copy code: base | extra_bits << 16
-  uint32_t scratch[40];             // table build: cnt[16], next[16]; code-length code: 18 lengths
-  uint8_t litq[kLitQ];              // literal ring, indexed by page-global literal index; doubles as
-                                    // the 512 x u16 code-length-code LUT while tables are read
-  alignas(16) uint8_t ring[kRing];  // output ring; doubles as the code-length array while tables are read
+  alignas(16) uint32_t scratch[160]; // table build: cnt[16], next[16], 18 code-length-code lengths;
+                                    // decode: [0..31] insert table, [32..159] copy table (uint4)
+  uint8_t litq[kLitQ];              // literal ring, indexed by page-global literal index
+  alignas(16) uint8_t ring[kRing];  // output ring; while tables are read: code lengths [0..727] and the
+                                    // 512 x u16 code-length-code LUT [1024..2047]
+  alignas(16) uint4 stage[4][32];   // compressed-input staging: 4 slots x 16 B per lane (cp.async ring)
 };
 
 // ---------------------------------------------------------------------------------------------
-// bit reader: lane-private, LSB first. Words are fetched from `base` (4-byte aligned start of the
-// page) with the index clamped to `lim` so that the deliberate over-read of the format
-// (BrotligDeswizzler.h:74-81) never leaves the stream buffer.
+// Input staging + bit reader. Every lane reads its own sub-stream strictly sequentially, so the
+// compressed bytes are streamed through a small per-lane ring in shared memory: 4 slots x 16 B,
+// filled with cp.async (LDGSTS: global -> shared without registers) two to three slots AHEAD of
+// the read position. A lane therefore never waits on an HBM/L2 round trip in the middle of a
+// dependent decode chain; a refill is one LDS. Chunk indices are clamped to the stream buffer, so
+// the deliberate over-read of the format (BrotligDeswizzler.h:74-81) never leaves it.
+BGX_DEV void cp_async16(void* smem_dst, const void* gmem_src) {
+#ifdef BGX_EMULATED
+  memcpy(smem_dst, gmem_src, 16);
+#else
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem_src) : "memory");
+#endif
+}
+BGX_DEV void cp_async_commit() {
+#ifndef BGX_EMULATED
+  asm volatile("cp.async.commit_group;\n" ::: "memory");
+#endif
+}
+template <int N>
+BGX_DEV void cp_async_wait() {
+#ifndef BGX_EMULATED
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+#endif
+}
+
 struct BitRd {
   uint32_t w0, w1, nxt;   // 64-bit window {w1:w0} and the prefetched next word
   uint32_t bitpos;        // < 32 between operations
-  uint32_t off;           // word index of the word after `nxt`
+  uint32_t k;             // index (from the lane's first 16-byte chunk) of the next word to fetch
 };
 
 struct PageIn {
+  // header access (a few broadcast loads at the start of a page)
   const uint32_t* base;   // page start (4-byte aligned)
-  uint32_t lim;           // largest word index that may be loaded
+  uint32_t lim;           // largest word index that may be loaded through `base`
+  // per-lane sub-stream staging
+  const uint4* g16;       // 16-byte aligned address at or below the page start
+  uint32_t lim16;         // largest chunk index that may be loaded through `g16`
+  uint32_t c0;            // chunk index (relative to g16) of this lane's chunk 0
+  uint4* stage;           // &WarpSmem::stage[0][lane]; slot s is stage[s * 32]
 };
 
 BGX_DEV uint32_t ld_word(const PageIn& in, uint32_t idx) { return in.base[idx < in.lim ? idx : in.lim]; }
 
-BGX_DEV void br_init(BitRd& r, const PageIn& in, uint32_t byte_off) {
-  const uint32_t w = byte_off >> 2;
-  r.w0 = ld_word(in, w);
-  r.w1 = ld_word(in, w + 1);
-  r.nxt = ld_word(in, w + 2);
-  r.off = w + 3;
-  r.bitpos = (byte_off & 3u) * 8u;
+BGX_DEV void stage_issue(const PageIn& in, uint32_t chunk) {   // chunk: index from the lane's chunk 0
+  const uint32_t g = in.c0 + chunk;
+  cp_async16(in.stage + (chunk & 3u) * 32u, in.g16 + (g < in.lim16 ? g : in.lim16));
+  cp_async_commit();
+}
+// Fetches word k of the lane's stream. When that was the last word of a chunk, the chunk three
+// ahead is requested into the slot of the chunk BEFORE this one (whose words were consumed long
+// ago), and the next chunk is guaranteed to have landed (at most 2 younger groups stay pending).
+BGX_DEV uint32_t stage_word(const PageIn& in, uint32_t k) {
+  const uint32_t v = reinterpret_cast<const uint32_t*>(in.stage + ((k >> 2) & 3u) * 32u)[k & 3u];
+  if ((k & 3u) == 3u) {
+    stage_issue(in, (k >> 2) + 3u);
+    cp_async_wait<2>();
+  }
+  return v;
+}
+
+BGX_DEV void br_init(BitRd& r, PageIn& in, uint32_t byte_off) {
+  // byte_off is relative to the page start; chunks are relative to g16
+  const uint32_t rel = (uint32_t)(reinterpret_cast<uintptr_t>(in.base) - reinterpret_cast<uintptr_t>(in.g16)) + byte_off;
+  in.c0 = rel >> 4;
+  stage_issue(in, 0);
+  stage_issue(in, 1);
+  stage_issue(in, 2);
+  cp_async_wait<0>();
+  const uint32_t k0 = (rel & 15u) >> 2;
+  r.w0 = stage_word(in, k0);
+  r.w1 = stage_word(in, k0 + 1);
+  r.nxt = stage_word(in, k0 + 2);
+  r.k = k0 + 3;
+  r.bitpos = (rel & 3u) * 8u;
 }
 BGX_DEV uint32_t br_peek(const BitRd& r) { return __funnelshift_r(r.w0, r.w1, r.bitpos); }  // 32 valid bits
 BGX_DEV void br_skip(BitRd& r, const PageIn& in, uint32_t n) {   // n <= 32
@@ -112,11 +176,12 @@ BGX_DEV void br_skip(BitRd& r, const PageIn& in, uint32_t n) {   // n <= 32
   if (r.bitpos >= 32u) {
     r.w0 = r.w1;
     r.w1 = r.nxt;
-    r.nxt = ld_word(in, r.off);
-    r.off += 1;
+    r.nxt = stage_word(in, r.k);
+    r.k += 1;
     r.bitpos -= 32u;
   }
 }
+BGX_DEV uint32_t shr32(uint32_t v, uint32_t n) { return n >= 32u ? 0u : (v >> n); }
 BGX_DEV uint32_t low_mask(uint32_t n) { return n >= 32u ? 0xffffffffu : ((1u << n) - 1u); }
 BGX_DEV uint32_t br_read(BitRd& r, const PageIn& in, uint32_t n) {   // n <= 32
   const uint32_t v = br_peek(r) & low_mask(n);
@@ -141,10 +206,19 @@ BGX_DEV uint32_t warp_incl_scan(uint32_t v, uint32_t lane) {
   return v;
 }
 
+BGX_DEV uint64_t warp_incl_scan64(uint64_t v, uint32_t lane) {   // two 32-bit scans in one shuffle chain
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint64_t t = __shfl_up_sync(kFull, v, d);
+    if (lane >= (uint32_t)d) v += t;
+  }
+  return v;
+}
+
 // ---------------------------------------------------------------------------------------------
 // prefix-code decode: primary LUT entry = symbol | length << 10; kLongCode => canonical search.
-template <int BITS>
-BGX_DEV uint32_t huff_decode(const uint16_t* lut, const HuffAux& aux, const uint16_t* sorted, uint32_t nsym,
+template <int BITS, typename SortedT>
+BGX_DEV uint32_t huff_decode(const uint16_t* lut, const HuffAux& aux, const SortedT* sorted, uint32_t nsym,
                              uint32_t peek, uint32_t& len) {
   const uint32_t e = lut[peek & ((1u << BITS) - 1u)];
   if (e != kLongCode) {
@@ -170,8 +244,8 @@ BGX_DEV void lut_fill_coop(uint16_t* lut, uint32_t rev, uint32_t len, uint16_t e
 
 // Builds LUT + canonical arrays from the code lengths in `lens[0..n)` (shared memory).
 // Canonical order = (length, symbol index), as GenerateHuffmanTable (BrotligHuffmanTable.cpp:44-71).
-template <int BITS>
-BGX_DEV void build_table(WarpSmem* sm, const uint8_t* lens, uint32_t n, uint16_t* lut, HuffAux& aux, uint16_t* sorted,
+template <int BITS, typename SortedT>
+BGX_DEV void build_table(WarpSmem* sm, const uint8_t* lens, uint32_t n, uint16_t* lut, HuffAux& aux, SortedT* sorted,
                          uint32_t lane) {
   uint32_t* cnt = sm->scratch;        // [16]
   uint32_t* next = sm->scratch + 16;  // [16] running position in `sorted` per length
@@ -207,7 +281,7 @@ BGX_DEV void build_table(WarpSmem* sm, const uint8_t* lens, uint32_t n, uint16_t
     __syncwarp();
     if (L && rank == 0) next[L] += __popc(m);
     if (L) {
-      if (idx < n) sorted[idx] = (uint16_t)s;
+      if (idx < n) sorted[idx] = (SortedT)s;
       if (L > (uint32_t)BITS) {
         const uint32_t prefix = code >> (L - BITS);
         lut[__brev(prefix) >> (32 - BITS)] = kLongCode;
@@ -233,9 +307,9 @@ BGX_DEV void build_table(WarpSmem* sm, const uint8_t* lens, uint32_t n, uint16_t
 
 // Reads one prefix-code description (trivial / simple / complex) and builds its tables.
 // Returns 0 or kPageErrTable. Cursor conventions: every table starts at sub-stream 0 (lane 0).
-template <int BITS>
+template <int BITS, typename SortedT>
 BGX_DEV uint32_t load_table(WarpSmem* sm, BitRd& rd, const PageIn& in, uint32_t alphabet, uint16_t* lut, HuffAux& aux,
-                            uint16_t* sorted, uint32_t lane) {
+                            SortedT* sorted, uint32_t lane) {
   const uint32_t max_bits = bgx::bit_length(alphabet - 1);
   uint32_t hdr = 0;
   if (lane == 0) hdr = br_read(rd, in, 6);
@@ -275,7 +349,7 @@ BGX_DEV uint32_t load_table(WarpSmem* sm, BitRd& rd, const PageIn& in, uint32_t 
   // order packed 5 bits each: 1,2,3,4,0,5,17,6,16,7,8,9,10,11,12,13,14,15
   const uint32_t kOrder[18] = {1, 2, 3, 4, 0, 5, 17, 6, 16, 7, 8, 9, 10, 11, 12, 13, 14, 15};
   uint32_t* cl_len_by_sym = sm->scratch + 16;   // [18] (next[] is not live yet)
-  uint16_t* cl_lut = reinterpret_cast<uint16_t*>(sm->litq);   // 512 entries: sym | len << 8
+  uint16_t* cl_lut = reinterpret_cast<uint16_t*>(sm->ring + 1024);   // 512 entries: sym | len << 8 (lens[] uses ring[0..727])
   uint32_t myread = 0;
   if (lane < 18) cl_len_by_sym[lane] = 0;   // the reference leaves these uninitialised when ncl < 18
   __syncwarp();
@@ -333,7 +407,7 @@ BGX_DEV uint32_t load_table(WarpSmem* sm, BitRd& rd, const PageIn& in, uint32_t 
     filled += __reduce_add_sync(kFull, active ? run : 0u);
   }
   __syncwarp();
-  build_table<BITS>(sm, lens, alphabet, lut, aux, sorted, lane);
+  build_table<BITS, SortedT>(sm, lens, alphabet, lut, aux, sorted, lane);
   return 0;
 }
 
@@ -387,6 +461,14 @@ BGX_DEV_NOINLINE PageResult decode_page_warp(const PageJob& job, WarpSmem* sm) {
   PageIn in;
   in.base = reinterpret_cast<const uint32_t*>(job.in);
   in.lim = (job.in_limit >> 2) ? (job.in_limit >> 2) - 1 : 0;
+  {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(job.in);
+    in.g16 = reinterpret_cast<const uint4*>(a & ~(uintptr_t)15);
+    const uint32_t span = (uint32_t)(a & 15u) + job.in_limit;       // bytes readable from g16
+    in.lim16 = (span >> 4) ? (span >> 4) - 1 : 0;
+    in.c0 = 0;
+    in.stage = &sm->stage[0][lane];
+  }
 
   // ---- length-code tables (RFC 7932 section 5)
   if (lane < 24) {
@@ -428,6 +510,10 @@ BGX_DEV_NOINLINE PageResult decode_page_warp(const PageJob& job, WarpSmem* sm) {
   __syncwarp();
 
   // ---- decode state (all uniform across the warp unless noted)
+#ifndef BGX_EMULATED
+  __builtin_assume(__isGlobal(job.out));
+  __builtin_assume(__isGlobal(job.in));
+#endif
   uint8_t* const out = job.out;
   const uint32_t out_size = job.out_size;
   const bool out_aligned = (reinterpret_cast<uintptr_t>(out) & 15u) == 0;
@@ -444,8 +530,8 @@ BGX_DEV_NOINLINE PageResult decode_page_warp(const PageJob& job, WarpSmem* sm) {
     // ================= 1. one command per lane, speculatively (lanes after the sentinel roll back)
     BitRd r = rd;
     uint32_t len;
-    uint32_t sym = huff_decode<kCmdLutBits>(sm->lut_cmd, sm->aux[0], sm->sorted_cmd, bgx::kNumCmdSymbols, br_peek(r), len);
-    br_skip(r, in, len);
+    const uint32_t pk = br_peek(r);
+    uint32_t sym = huff_decode<kCmdLutBits>(sm->lut_cmd, sm->aux[0], sm->sorted_cmd, bgx::kNumCmdSymbols, pk, len);
     const uint32_t sent = __ballot_sync(kFull, sym == (uint32_t)bgx::kCmdSentinel);
     const uint32_t n = sent ? (uint32_t)(__ffs((int)sent) - 1) : 32u;   // commands in this round
     done = sent != 0;
@@ -462,36 +548,52 @@ BGX_DEV_NOINLINE PageResult decode_page_warp(const PageJob& job, WarpSmem* sm) {
         if (ic > 23u) ic = 23u;
       }
       const uint32_t ei = sm->lenlut[ic];
-      ins = (ei & 0xffffu) + br_read(r, in, ei >> 16);
+      const uint32_t ec = has_copy ? sm->lenlut[24 + cc] : 0u;
+      const uint32_t nbi = ei >> 16, nbc = ec >> 16;
+      if (len + nbi + nbc <= 32u) {   // symbol + both extra-bit fields out of the one 32-bit peek
+        ins = (ei & 0xffffu) + (shr32(pk, len) & low_mask(nbi));
+        cpy = (ec & 0xffffu) + (shr32(pk, len + nbi) & low_mask(nbc));
+        br_skip(r, in, len + nbi + nbc);
+      } else {                        // 24-bit extras: field by field
+        br_skip(r, in, len);
+        ins = (ei & 0xffffu) + br_read(r, in, nbi);
+        cpy = (ec & 0xffffu) + br_read(r, in, nbc);
+      }
       if (has_copy) {
-        const uint32_t ec = sm->lenlut[24 + cc];
-        cpy = (ec & 0xffffu) + br_read(r, in, ec >> 16);
         if (sym >= 128u) {
-          dcode = huff_decode<kDistLutBits>(sm->lut_dist, sm->aux[1], sm->sorted_dist, bgx::kNumDistSymbols, br_peek(r), len);
-          br_skip(r, in, len);
-        }
-        if (dcode >= 16u) {   // explicit distance (PageDecoder.cpp:367-394)
-          if (ndirect > 0 && dcode < 16u + ndirect) {
-            dist = dcode - 15u;
-          } else {
+          const uint32_t pk2 = br_peek(r);
+          dcode = huff_decode<kDistLutBits>(sm->lut_dist, sm->aux[1], sm->sorted_dist, bgx::kNumDistSymbols, pk2, len);
+          if (dcode >= 16u + ndirect) {   // explicit distance with extra bits (PageDecoder.cpp:376-394)
             const uint32_t v = dcode - ndirect - 16u;
             uint32_t nb = 1u + (v >> (npostfix + 1u));
             if (nb > 24u) nb = 24u;
-            const uint32_t extra = br_read(r, in, nb);
+            uint32_t extra;
+            if (len + nb <= 32u) {
+              extra = shr32(pk2, len) & low_mask(nb);
+              br_skip(r, in, len + nb);
+            } else {
+              br_skip(r, in, len);
+              extra = br_read(r, in, nb);
+            }
             const uint32_t h = v >> npostfix, lo = v & ((1u << npostfix) - 1u);
             dist = ((((2u + (h & 1u)) << nb) - 4u + extra) << npostfix) + lo + ndirect + 1u;
+          } else {
+            br_skip(r, in, len);
+            if (dcode >= 16u) dist = dcode - 15u;   // direct distance codes (PageDecoder.cpp:369-373)
           }
         }
       }
       rd = r;
     } else if (lane == n) {
+      br_skip(r, in, len);
       rd = r;   // the sentinel's code bits are consumed; its lane then continues with literals
     }
 
     // ================= 2. positions
     const uint32_t tot = ins + cpy;
-    const uint32_t incl_tot = warp_incl_scan(tot, lane);
-    const uint32_t incl_ins = warp_incl_scan(ins, lane);
+    const uint64_t incl_both = warp_incl_scan64(((uint64_t)tot << 32) | ins, lane);
+    const uint32_t incl_tot = (uint32_t)(incl_both >> 32);
+    const uint32_t incl_ins = (uint32_t)incl_both;
     const uint32_t round_out = __shfl_sync(kFull, incl_tot, 31);
     const uint32_t round_ins = __shfl_sync(kFull, incl_ins, 31);
     const uint32_t o_ins = pos + incl_tot - tot;        // where this command's literals go
@@ -528,6 +630,7 @@ BGX_DEV_NOINLINE PageResult decode_page_warp(const PageJob& job, WarpSmem* sm) {
       const uint32_t carry_val = cslot == 0 ? r0 : cslot == 1 ? r1 : cslot == 2 ? r2 : r3;
       uint32_t resolved = __ballot_sync(kFull, !unresolved);
       while (resolved != kFull) {
+        BGX_STAT(emu_stats().ring_iters++);
         const uint32_t v = __shfl_sync(kFull, dist, src_lane);
         const bool ready = unresolved && (from_carry || ((resolved >> src_lane) & 1u));
         if (ready) {
@@ -561,40 +664,104 @@ BGX_DEV_NOINLINE PageResult decode_page_warp(const PageJob& job, WarpSmem* sm) {
     uint32_t mine = rl > lane ? (rl - lane + 31u) >> 5 : 0u;
     const bool fast = round_out <= kRoundMax && avail + rl <= kLitQ;
 
+    BGX_STAT(emu_stats().rounds++; emu_stats().lits += rl; if (!fast) emu_stats().slow_rounds++);
     if (fast) {
+#ifdef BGX_STATS
+      {
+        const uint32_t mi = __reduce_max_sync(kFull, ins < kCoopLen ? ins : 0u);
+        const uint32_t ncp = __popc(__ballot_sync(kFull, cpy != 0));
+        const uint32_t far = __reduce_add_sync(kFull, (cpy && dist > 3000u) ? cpy : 0u);
+        const uint32_t ov = __popc(__ballot_sync(kFull, cpy != 0 && dist < cpy));
+        BGX_STAT(emu_stats().sum_max_ins += mi; emu_stats().ins_bytes += round_ins; emu_stats().copies += ncp;
+                 emu_stats().copy_bytes += round_out - round_ins; emu_stats().far_bytes += far; emu_stats().overlap_copies += ov);
+      }
+#endif
       decode_literals(sm, rd, in, lit_tail, mine, lane);
       lit_tail += rl;
       __syncwarp();
       const int32_t ring_lo = ring_from > (int32_t)round_end - (int32_t)kRing ? ring_from : (int32_t)round_end - (int32_t)kRing;
 
-      // ---- 5. inserts: short ones lane-per-command, long ones by the whole warp
-      if (ins && ins < kCoopLen) {
-        uint32_t q = lq & (kLitQ - 1), p = o_ins & (kRing - 1);
-        for (uint32_t j = 0; j < ins; ++j) {
-          sm->ring[p] = sm->litq[q];
-          q = (q + 1) & (kLitQ - 1);
-          p = (p + 1) & (kRing - 1);
+      // ---- 5. inserts, flattened: lane t places literal t of the round (perfectly balanced, any length).
+      //         Commands with literals are compacted into tab[]; a per-chunk bit mask of their first
+      //         literal index turns "which command owns literal t" into one popc.
+      uint32_t* tab = sm->scratch;                       // [32] (o_ins - first literal index)
+      uint4* tab2 = reinterpret_cast<uint4*>(sm->scratch + 32);   // [32] (dst - first flat index, distance, dst start)
+      const uint32_t le_mask = 0xffffffffu >> (31u - lane);
+      {
+        const uint32_t has = __ballot_sync(kFull, ins != 0);
+        const uint32_t S = incl_ins - ins;               // round-local index of this command's first literal
+        if (ins) tab[__popc(has & lt_mask)] = o_ins - S;
+        __syncwarp();
+        uint32_t before = 0;
+        for (uint32_t c0 = 0; c0 < round_ins; c0 += 32) {
+          const uint32_t M = __reduce_or_sync(kFull, (ins && S - c0 < 32u) ? (1u << (S - c0)) : 0u);
+          const uint32_t t = c0 + lane;
+          if (t < round_ins) {
+            const uint32_t ord = before + __popc(M & le_mask) - 1u;
+            sm->ring[(tab[ord] + t) & (kRing - 1)] = sm->litq[(lit_head + t) & (kLitQ - 1)];
+          }
+          before += __popc(M);
         }
-      }
-      uint32_t big = __ballot_sync(kFull, ins >= kCoopLen);
-      while (big) {
-        const int k = __ffs((int)big) - 1;
-        big &= big - 1;
-        const uint32_t n_k = __shfl_sync(kFull, ins, k);
-        const uint32_t o_k = __shfl_sync(kFull, o_ins, k);
-        const uint32_t q_k = __shfl_sync(kFull, lq, k);
-        for (uint32_t j = lane; j < n_k; j += 32) sm->ring[(o_k + j) & (kRing - 1)] = sm->litq[(q_k + j) & (kLitQ - 1)];
       }
       __syncwarp();
 
-      // ---- 6. copies in dependency wavefronts
+      // ---- 6. copies. Wavefront 1 (flattened, like the inserts): every copy whose source already is
+      //         final -- it lies below the destination of the first pending copy -- and that does not
+      //         overlap its own destination. Sources may be in the ring or (far matches) in L1/L2.
       const uint32_t src_lo = o_cpy - dist;                              // first source byte
       const uint32_t src_hi = src_lo + (cpy < dist ? cpy : dist);        // one past the last distinct source byte
       uint32_t pending = __ballot_sync(kFull, cpy != 0);
-      while (pending) {
+      if (pending) {
         const int first = __ffs((int)pending) - 1;
         const uint32_t hwm = __shfl_sync(kFull, o_cpy, first);           // everything below is final
+        const bool ready1 = cpy != 0 && ((int)lane == first || src_hi <= hwm);
+        const uint32_t len1 = ready1 ? cpy : 0u;
+        const uint32_t E1 = warp_incl_scan(len1, lane);
+        const uint32_t T1 = __shfl_sync(kFull, E1, 31);
+        const uint32_t S1 = E1 - len1;
+        const uint32_t m1 = __ballot_sync(kFull, ready1);
+        if (ready1) tab2[__popc(m1 & lt_mask)] = make_uint4(o_cpy - S1, dist, o_cpy, 0u);
+        __syncwarp();
+        uint32_t before = 0;
+        for (uint32_t c0 = 0; c0 < T1; c0 += 128) {      // four 32-byte chunks per trip: all loads go out before the stores
+          uint32_t d[4];
+          uint8_t v[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const uint32_t cu = c0 + 32u * u;
+            const uint32_t M = __reduce_or_sync(kFull, (ready1 && S1 - cu < 32u) ? (1u << (S1 - cu)) : 0u);
+            const uint32_t t = cu + lane;
+            d[u] = 0xffffffffu;
+            v[u] = 0;
+            if (t < T1) {
+              const uint4 p = tab2[before + __popc(M & le_mask) - 1u];
+              d[u] = p.x + t;
+              uint32_t j = d[u] - p.z;            // byte index inside the copy
+              if (j >= p.y) j %= p.y;             // overlapping copy: pattern of `dist` bytes repeats (PageDecoder.cpp:222-232)
+              v[u] = out_byte(sm, out, ring_lo, p.z - p.y + j);
+            }
+            before += __popc(M);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (d[u] != 0xffffffffu) sm->ring[d[u] & (kRing - 1)] = v[u];
+        }
+        __syncwarp();
+        pending &= ~m1;
+      }
+      //         Remaining copies (dependent on this round's copies, or overlapping themselves): in
+      //         wavefronts, one lane per command, byte-serial.
+      while (pending) {
+        const int first = __ffs((int)pending) - 1;
+        const uint32_t hwm = __shfl_sync(kFull, o_cpy, first);
         const bool ready = ((pending >> lane) & 1u) && ((int)lane == first || src_hi <= hwm);
+#ifdef BGX_STATS
+        {
+          const uint32_t mc = __reduce_max_sync(kFull, (ready && cpy < kCoopLen) ? cpy : 0u);
+          const uint32_t nc = __popc(__ballot_sync(kFull, ready && cpy >= kCoopLen));
+          BGX_STAT(emu_stats().wavefronts++; emu_stats().sum_max_cpy += mc; emu_stats().coop_copies += nc);
+        }
+#endif
         if (ready && cpy < kCoopLen) {
           // byte-serial, so an overlapping copy (dist < len) replicates its pattern exactly as
           // PageDecoder.cpp:222-232 does: later bytes read what this loop has just written

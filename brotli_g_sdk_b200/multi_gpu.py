@@ -87,7 +87,8 @@ def decode_sharded_stream(stream_on_owner, owner: int, decode_fn: Callable, devi
     # the control plane (not the data path). Callers that know the size can skip it via broadcast_stream().
     dist.broadcast(meta, src=owner, group=group)
     n = int(meta.item())
-    buf = stream_on_owner if rank == owner else torch.empty(n + 64, dtype=torch.uint8, device=dev)
+    # receive buffer: 16-byte aligned (torch allocations are) and padded to the 16-byte staging granularity
+    buf = stream_on_owner if rank == owner else torch.zeros(((n + 15) // 16) * 16 + 64, dtype=torch.uint8, device=dev)
     payload = buf[:n]
     dist.broadcast(payload, src=owner, group=group)          # <- the one data-path collective
     geo = StreamGeometry.parse(bytes(payload[:16].cpu().numpy()))
@@ -105,6 +106,11 @@ def cuda_decode_fn(decoder):
         out = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=buf.device)
         if nbytes == 0:
             return out[:0]
+        need = ((n + 15) // 16) * 16
+        if int(buf.numel()) < need or buf.data_ptr() % 16:      # the kernel stages input in aligned 16-byte chunks
+            padded = torch.zeros(need + 64, dtype=torch.uint8, device=buf.device)
+            padded[:n].copy_(buf[:n])
+            buf = padded
         plan = decoder.plan([dict(d_src=buf.data_ptr(), src_size=n, src_capacity=int(buf.numel()), d_dst=out.data_ptr(),
                                   dst_capacity=nbytes, header=bytes(buf[:16].cpu().numpy()), page_begin=lo, page_count=hi - lo)])
         # run on a side stream ordered after whatever produced `buf` (e.g. the NCCL broadcast)

@@ -46,9 +46,9 @@ int bgx_decode_batch_host(bgx_context* ctx, uint32_t n, const uint8_t* const* in
 
 /* ---- device-resident interface (no host<->device traffic in the decode path) ---- */
 typedef struct bgx_stream {
-  const uint8_t* d_src;      /* device pointer to the stream (4-byte aligned) */
+  const uint8_t* d_src;      /* device pointer to the stream (16-byte aligned) */
   uint32_t src_size;         /* stream bytes */
-  uint32_t src_capacity;     /* readable bytes at d_src (>= src_size); the kernel never reads beyond it */
+  uint32_t src_capacity;     /* readable bytes at d_src, >= src_size rounded up to 16; the kernel never reads beyond it */
   uint8_t* d_dst;            /* device pointer: where page `page_begin` of the stream is written */
   uint32_t dst_capacity;     /* writable bytes at d_dst */
   uint32_t page_begin;       /* first page to decode */

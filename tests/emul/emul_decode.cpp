@@ -15,6 +15,12 @@ extern "C" {
 // status_out[page] receives the kernel status, flags_out[page] the delta flag. Returns a BROTLIG_ERROR.
 int emul_decode_stream(const uint8_t* src, uint32_t src_size, uint8_t* dst, uint32_t dst_capacity, uint32_t* status_out,
                        uint32_t* flags_out, uint64_t* collectives_out) {
+  // the device path requires 16-byte aligned stream buffers (cp.async staging): give it one
+  std::vector<uint8_t> aligned_buf(src_size + 64 + 80);
+  uint8_t* al = aligned_buf.data() + ((64 - (reinterpret_cast<uintptr_t>(aligned_buf.data()) & 63)) & 63);
+  memcpy(al, src, src_size);
+  memset(al + src_size, 0xDB, 64);
+  src = al;
   bgx::StreamInfo si;
   const int rc = bgx::parse_stream_header(src, &si);
   if (rc) return rc;
@@ -52,7 +58,7 @@ int emul_decode_stream(const uint8_t* src, uint32_t src_size, uint8_t* dst, uint
       bgxk::PageJob job;
       job.in = pages + e.in_off;
       job.in_size = e.in_size;
-      job.in_limit = (uint32_t)((src + src_size) - (pages + e.in_off));
+      job.in_limit = (uint32_t)((src + src_size + 16) - (pages + e.in_off));
       job.out = dst + e.out_off;
       job.out_size = e.out_size;
       job.allow_delta = si.preconditioned;
@@ -79,5 +85,11 @@ int emul_decode_stream(const uint8_t* src, uint32_t src_size, uint8_t* dst, uint
   return worst;
 }
 
+#ifdef BGX_STATS
+void emul_stats(uint64_t* out14, int reset) {
+  memcpy(out14, &bgxk::emu_stats(), sizeof(bgxk::EmuStats));
+  if (reset) memset(&bgxk::emu_stats(), 0, sizeof(bgxk::EmuStats));
+}
+#endif
 uint32_t emul_warp_smem_bytes() { return (uint32_t)sizeof(bgxk::WarpSmem); }
 }

@@ -291,5 +291,7 @@ template <typename T>
 inline T atomicOr(T* p, T v) { T old = *p; *p = old | v; return old; }
 template <typename T>
 inline T atomicMax(T* p, T v) { T old = *p; if (v > old) *p = v; return old; }
-struct uint4 { unsigned x, y, z, w; };
+struct alignas(16) uint4 { unsigned x, y, z, w; };
 struct uint2 { unsigned x, y; };
+inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { uint4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
+inline uint2 make_uint2(unsigned x, unsigned y) { uint2 r; r.x = x; r.y = y; return r; }
