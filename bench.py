@@ -317,13 +317,14 @@ def run_ours(args):
     value = world * out_bytes / (ms_step / 1e3) / 1e9
     peak, peak_src = measured_peak_gbs()
     achieved = (in_bytes + out_bytes) / (ms_step / 1e3) / 1e9     # per GPU
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tp):
+    def ncu_traffic(kind, algorithmic_bytes):
+        # DRAM bytes per launch from the committed ncu capture (profiles/traffic.json), scaled to this launch
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
         try:
-            traffic = json.load(open(tp)).get(args.workload)
+            return float(json.load(open(tp))[kind]["ratio_to_algorithmic"]) * algorithmic_bytes
         except Exception:
-            traffic = None
+            return None
+    traffic = ncu_traffic(args.workload, in_bytes + out_bytes)
     launches_per_step = plan.info["kernels_per_launch"]
 
     # ---------------- end to end through the host-pointer C-ABI call (pinned host buffers)
@@ -368,7 +369,7 @@ def run_ours(args):
                                  f"({rep2['unique_streams']} unique x {rep2['replicas']} replicas in distinct HBM buffers)",
                      "value": world * o2 / (ms2 / 1e3) / 1e9, "unit": "GB/s", "ms_per_step": ms2, "compression_ratio": o2 / i2,
                      "roofline": {"bound": "hbm", "achieved": (i2 + o2) / (ms2 / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
-                                  "frac": (i2 + o2) / (ms2 / 1e3) / 1e9 / peak, "traffic": None}}
+                                  "frac": (i2 + o2) / (ms2 / 1e3) / 1e9 / peak, "traffic": ncu_traffic("mixed", i2 + o2)}}
         del keep2, plan2
 
     # ---------------- CPU baseline (rank 0, N = 1 only): reference DecodeCPU on a bounded sample
