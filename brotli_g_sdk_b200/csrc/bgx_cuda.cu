@@ -42,16 +42,19 @@ struct QueueCtl {
   uint32_t bad_pages;       // pages whose decode reported an error
 };
 
-__global__ void __launch_bounds__(32) bgx_decode_pages_kernel(const StreamDev* __restrict__ streams, uint32_t nstreams,
-                                                              uint32_t total_pages, QueueCtl* ctl,
-                                                              uint32_t* __restrict__ page_status) {
+constexpr int kPageThreads = 64;   // two warps per page: producer (entropy decode) + consumer (LZ77 assembly)
+
+__global__ void __launch_bounds__(kPageThreads) bgx_decode_pages_kernel(const StreamDev* __restrict__ streams, uint32_t nstreams,
+                                                                        uint32_t q_begin, uint32_t q_end, QueueCtl* ctl,
+                                                                        uint32_t* __restrict__ page_status) {
   __shared__ bgxk::WarpSmem sm;
-  const uint32_t lane = threadIdx.x;
+  __shared__ uint32_t q_shared;
+  const uint32_t tid = threadIdx.x;
   for (;;) {
-    uint32_t q = 0;
-    if (lane == 0) q = atomicAdd(&ctl->next_page, 1u);
-    q = __shfl_sync(bgxk::kFull, q, 0);
-    if (q >= total_pages) break;
+    if (tid == 0) q_shared = atomicAdd(&ctl->next_page, 1u);
+    __syncthreads();
+    const uint32_t q = q_begin + q_shared;   // [q_begin, q_end): the slice of the flat page queue this launch owns
+    if (q >= q_end) break;
     // stream owning queue slot q: last stream with first_q <= q
     uint32_t lo = 0, hi = nstreams;
     while (hi - lo > 1) {
@@ -69,7 +72,7 @@ __global__ void __launch_bounds__(32) bgx_decode_pages_kernel(const StreamDev* _
     uint8_t* out = s.dst + (size_t)(page - s.page_begin) * s.page_size;
     uint32_t status = 0;
     if (e.in_size == e.out_size) {
-      bgxk::copy_page_warp(out, in, e.out_size);
+      bgxk::copy_page_cta(out, in, e.out_size);
     } else {
       bgxk::PageJob job;
       job.in = in;
@@ -82,20 +85,19 @@ __global__ void __launch_bounds__(32) bgx_decode_pages_kernel(const StreamDev* _
       if (e.in_size < 8u || in + e.in_size > s.src_end) {
         status = bgxk::kPageErrTable;
       } else {
-        const bgxk::PageResult r = bgxk::decode_page_warp(job, &sm);
+        const bgxk::PageResult r = bgxk::decode_page_cta(job, &sm);
         status = r.status;
         if (!status && r.is_delta) {
-          __syncwarp();
-          bgxk::delta_decode_warp(out, e.out_off, e.out_size, s.planes);
+          if (tid >= 32) bgxk::delta_decode_warp(out, e.out_off, e.out_size, s.planes);   // the consumer warp wrote the page
           status |= 0x40000000u;   // informational: page was delta coded
         }
       }
     }
-    if (lane == 0) {
+    if (tid == 0) {
       page_status[q] = status;
       if (status & 0xffffu) atomicAdd(&ctl->bad_pages, 1u);
     }
-    __syncwarp();
+    __syncthreads();   // q_shared and the page arena are reused by the next page
   }
 }
 
@@ -111,7 +113,7 @@ __global__ void __launch_bounds__(256) bgx_decondition_kernel(const PreconLayout
 // ------------------------------------------------------------------------------------ host side
 struct bgx_context {
   int device = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr, s_in = nullptr, s_out = nullptr;   // kernels / uploads / downloads
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int sm_count = 0;
   int blocks_per_sm = 0;
@@ -124,6 +126,7 @@ struct bgx_context {
 };
 
 struct PreconJob {
+  uint32_t stream_index = 0;      // position of the stream in the caller's list
   PreconLayout layout;
   PreconLayout* d_layout = nullptr;
   uint8_t* d_planes = nullptr;    // conditioned scratch (decode target)
@@ -142,7 +145,10 @@ struct bgx_plan {
   uint8_t* d_scratch = nullptr;   // backing store of all conditioned scratch planes
   bgx_plan_info info{};
   cudaStream_t last_stream = nullptr;
+  std::vector<uint32_t> q_start;  // [n+1]: first queue slot of caller stream i (prefix sum of its page count)
+  uint32_t groups_used = 1;
 };
+constexpr uint32_t kMaxGroups = 64;
 
 namespace {
 
@@ -197,6 +203,8 @@ int bgx_create(bgx_context** out, int device) {
   if (e != cudaSuccess) { fprintf(stderr, "brotlig_b200: cudaGetDeviceProperties: %s\n", cudaGetErrorString(e)); delete ctx; return bgx::kErrGeneric; }
   ctx->sm_count = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
     fprintf(stderr, "brotlig_b200: stream/event creation failed\n");
     delete ctx;
@@ -205,7 +213,7 @@ int bgx_create(bgx_context** out, int device) {
   // one-warp CTAs, as many as the shared-memory arena allows per SM
   cudaFuncSetAttribute(bgx_decode_pages_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   int per_sm = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bgx_decode_pages_kernel, 32, 0);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bgx_decode_pages_kernel, kPageThreads, 0);
   if (e != cudaSuccess || per_sm < 1) {
     fprintf(stderr, "brotlig_b200: kernel image not usable on this device (%s); built for sm_100a\n", cudaGetErrorString(e));
     delete ctx;
@@ -224,6 +232,8 @@ void bgx_destroy(bgx_context* ctx) {
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
+  if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
   delete ctx;
 }
 
@@ -249,7 +259,10 @@ int bgx_plan_create(bgx_context* ctx, const bgx_stream* streams, uint32_t n, bgx
   struct Guard { bgx_plan* p; ~Guard() { if (p) bgx_plan_destroy(p); } } guard{plan};
   uint64_t scratch_bytes = 0;
   std::vector<size_t> scratch_off;
+  plan->q_start.assign(n + 1, 0);
   for (uint32_t i = 0; i < n; ++i) {
+    plan->q_start[i] = plan->total_pages;
+    plan->q_start[i + 1] = plan->total_pages;
     const bgx_stream& s = streams[i];
     StreamInfo si;
     const int rc = bgx::parse_stream_header(s.header, &si);
@@ -301,12 +314,14 @@ int bgx_plan_create(bgx_context* ctx, const bgx_stream* streams, uint32_t n, bgx
       }
       scratch_off.push_back((size_t)scratch_bytes);
       scratch_bytes += ((uint64_t)si.uncompressed_size + 255u) & ~255ull;
+      pj.stream_index = i;
       plan->precon.push_back(pj);
       d.dst = nullptr;   // patched below once the scratch arena exists
       d.allow_delta = 1u | ((uint32_t)plan->precon.size() << 8);   // remember which precon job (index+1) in the high bits
     }
     plan->h_streams.push_back(d);
     plan->total_pages += count;
+    plan->q_start[i + 1] = plan->total_pages;
     plan->info.compressed_bytes += s.src_size;   // whole-stream bytes; page ranges read a subset (reported as upper bound)
     plan->info.uncompressed_bytes += produced;
   }
@@ -330,11 +345,11 @@ int bgx_plan_create(bgx_context* ctx, const bgx_stream* streams, uint32_t n, bgx
   BGX_CUDA(ctx, cudaMalloc(&plan->d_streams, ns * sizeof(StreamDev)));
   if (!plan->h_streams.empty())
     BGX_CUDA(ctx, cudaMemcpy(plan->d_streams, plan->h_streams.data(), plan->h_streams.size() * sizeof(StreamDev), cudaMemcpyHostToDevice));
-  BGX_CUDA(ctx, cudaMalloc(&plan->d_ctl, sizeof(QueueCtl)));
+  BGX_CUDA(ctx, cudaMalloc(&plan->d_ctl, kMaxGroups * sizeof(QueueCtl)));
   BGX_CUDA(ctx, cudaMalloc(&plan->d_status, std::max<size_t>(plan->total_pages, 1) * sizeof(uint32_t)));
   plan->info.kernels_per_launch = (plan->total_pages ? 1u : 0u) + (uint32_t)plan->precon.size();
   plan->info.sm_count = (uint32_t)ctx->sm_count;
-  plan->info.block_threads = 32;
+  plan->info.block_threads = kPageThreads;
   plan->info.smem_bytes_per_block = (uint32_t)sizeof(bgxk::WarpSmem);
   const uint64_t max_blocks = (uint64_t)ctx->sm_count * ctx->blocks_per_sm;
   plan->info.grid_blocks = (uint32_t)std::min<uint64_t>(max_blocks, std::max<uint32_t>(plan->total_pages, 1));
@@ -343,18 +358,22 @@ int bgx_plan_create(bgx_context* ctx, const bgx_stream* streams, uint32_t n, bgx
   return bgx::kOk;
 }
 
-int bgx_plan_launch(bgx_context* ctx, bgx_plan* plan, void* cuda_stream) {
-  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
-  plan->last_stream = st;
-  BGX_CUDA(ctx, cudaMemsetAsync(plan->d_ctl, 0, sizeof(QueueCtl), st));
+// Enqueues the decode of caller streams [a, b) on `st`, using work-queue control block `group`.
+static int launch_range(bgx_context* ctx, bgx_plan* plan, uint32_t a, uint32_t b, uint32_t group, cudaStream_t st) {
+  const uint32_t q0 = plan->q_start[a], q1 = plan->q_start[b];
+  BGX_CUDA(ctx, cudaMemsetAsync(plan->d_ctl + group, 0, sizeof(QueueCtl), st));
   for (auto& p : plan->precon)
-    if (p.has_padding) BGX_CUDA(ctx, cudaMemsetAsync(p.d_tex, 0, p.out_size, st));   // pitch padding stays 0 (BrotligDecoder.cpp:448)
-  if (plan->total_pages) {
-    bgx_decode_pages_kernel<<<plan->info.grid_blocks, 32, 0, st>>>(plan->d_streams, (uint32_t)plan->h_streams.size(),
-                                                                   plan->total_pages, plan->d_ctl, plan->d_status);
+    if (p.stream_index >= a && p.stream_index < b && p.has_padding)
+      BGX_CUDA(ctx, cudaMemsetAsync(p.d_tex, 0, p.out_size, st));   // pitch padding stays 0 (BrotligDecoder.cpp:448)
+  if (q1 > q0) {
+    const uint64_t max_blocks = (uint64_t)ctx->sm_count * ctx->blocks_per_sm;
+    const uint32_t grid = (uint32_t)std::min<uint64_t>(max_blocks, q1 - q0);
+    bgx_decode_pages_kernel<<<grid, kPageThreads, 0, st>>>(plan->d_streams, (uint32_t)plan->h_streams.size(), q0, q1,
+                                                 plan->d_ctl + group, plan->d_status);
     BGX_CUDA(ctx, cudaGetLastError());
   }
   for (auto& p : plan->precon) {
+    if (p.stream_index < a || p.stream_index >= b) continue;
     const uint32_t blocks = (p.layout.total_blocks + 255u) / 256u;
     if (blocks) bgx_decondition_kernel<<<blocks, 256, 0, st>>>(p.d_layout, p.d_planes, p.d_tex);
     BGX_CUDA(ctx, cudaGetLastError());
@@ -362,12 +381,21 @@ int bgx_plan_launch(bgx_context* ctx, bgx_plan* plan, void* cuda_stream) {
   return bgx::kOk;
 }
 
+int bgx_plan_launch(bgx_context* ctx, bgx_plan* plan, void* cuda_stream) {
+  cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+  plan->last_stream = st;
+  plan->groups_used = 1;
+  return launch_range(ctx, plan, 0, (uint32_t)plan->q_start.size() - 1, 0, st);
+}
+
 int bgx_plan_finish(bgx_context* ctx, bgx_plan* plan, uint32_t* bad_pages) {
-  QueueCtl h{};
+  QueueCtl h[kMaxGroups];
   BGX_CUDA(ctx, cudaStreamSynchronize(plan->last_stream ? plan->last_stream : ctx->stream));
-  BGX_CUDA(ctx, cudaMemcpy(&h, plan->d_ctl, sizeof h, cudaMemcpyDeviceToHost));
-  if (bad_pages) *bad_pages = h.bad_pages;
-  if (h.bad_pages) { ctx->err = std::to_string(h.bad_pages) + " page(s) failed to decode"; return bgx::kErrCorruptStream; }
+  BGX_CUDA(ctx, cudaMemcpy(h, plan->d_ctl, plan->groups_used * sizeof(QueueCtl), cudaMemcpyDeviceToHost));
+  uint32_t bad = 0;
+  for (uint32_t g = 0; g < plan->groups_used; ++g) bad += h[g].bad_pages;
+  if (bad_pages) *bad_pages = bad;
+  if (bad) { ctx->err = std::to_string(bad) + " page(s) failed to decode"; return bgx::kErrCorruptStream; }
   return bgx::kOk;
 }
 
@@ -393,7 +421,6 @@ int bgx_decode_batch_host(bgx_context* ctx, uint32_t n, const uint8_t* const* in
   if (grow(ctx, &ctx->d_in, &ctx->d_in_cap, in_total)) return bgx::kErrGeneric;
   if (grow(ctx, &ctx->d_out, &ctx->d_out_cap, out_total)) return bgx::kErrGeneric;
   for (uint32_t i = 0; i < n; ++i) {
-    BGX_CUDA(ctx, cudaMemcpyAsync(ctx->d_in + in_off[i], inputs[i], input_sizes[i], cudaMemcpyHostToDevice, ctx->stream));
     bgx_stream& s = st[i];
     memset(&s, 0, sizeof s);
     s.d_src = ctx->d_in + in_off[i];
@@ -406,19 +433,56 @@ int bgx_decode_batch_host(bgx_context* ctx, uint32_t n, const uint8_t* const* in
   bgx_plan* plan = nullptr;
   int rc = bgx_plan_create(ctx, st.data(), n, &plan);
   if (rc) return rc;
-  cudaEventRecord(ctx->ev0, ctx->stream);
-  rc = bgx_plan_launch(ctx, plan, ctx->stream);
-  cudaEventRecord(ctx->ev1, ctx->stream);
-  if (!rc) {
-    for (uint32_t i = 0; i < n; ++i)
-      if (usize[i]) cudaMemcpyAsync(outputs[i], ctx->d_out + out_off[i], usize[i], cudaMemcpyDeviceToHost, ctx->stream);
-    rc = bgx_plan_finish(ctx, plan, nullptr);
+  // Three-stage pipeline over groups of streams: upload (s_in) -> kernels (ctx->stream) -> download (s_out).
+  // Uploads and downloads run concurrently on the two PCIe directions; the reference host serialises
+  // upload -> dispatch -> readback (BrotligGPUDecoder.cpp:633-727).
+  std::vector<uint32_t> cut{0};
+  {
+    const size_t total = in_total + out_total;
+    const size_t target = std::max<size_t>(48u << 20, total / 12);
+    size_t acc = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+      acc += (size_t)input_sizes[i] + usize[i];
+      if ((acc >= target && cut.size() < kMaxGroups) || i + 1 == n) { cut.push_back(i + 1); acc = 0; }
+    }
   }
+  const uint32_t G = (uint32_t)cut.size() - 1;
+  plan->groups_used = G;
+  std::vector<cudaEvent_t> ev(3 * (size_t)G);
+  for (auto& e : ev) cudaEventCreate(&e);
+  cudaEvent_t ev_start;
+  cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming);
+  cudaEventRecord(ev_start, ctx->stream);              // arena growth / earlier work on the context stream
+  cudaStreamWaitEvent(ctx->s_in, ev_start, 0);
+  cudaStreamWaitEvent(ctx->s_out, ev_start, 0);
+  for (uint32_t g = 0; g < G && !rc; ++g) {
+    cudaEvent_t e_in = ev[3 * g], e_k0 = ev[3 * g + 1], e_k1 = ev[3 * g + 2];
+    for (uint32_t i = cut[g]; i < cut[g + 1]; ++i)
+      cudaMemcpyAsync(ctx->d_in + in_off[i], inputs[i], input_sizes[i], cudaMemcpyHostToDevice, ctx->s_in);
+    cudaEventRecord(e_in, ctx->s_in);
+    cudaStreamWaitEvent(ctx->stream, e_in, 0);
+    cudaEventRecord(e_k0, ctx->stream);
+    rc = launch_range(ctx, plan, cut[g], cut[g + 1], g, ctx->stream);
+    cudaEventRecord(e_k1, ctx->stream);
+    cudaStreamWaitEvent(ctx->s_out, e_k1, 0);
+    for (uint32_t i = cut[g]; i < cut[g + 1]; ++i)
+      if (usize[i]) cudaMemcpyAsync(outputs[i], ctx->d_out + out_off[i], usize[i], cudaMemcpyDeviceToHost, ctx->s_out);
+  }
+  cudaStreamSynchronize(ctx->s_in);
+  cudaStreamSynchronize(ctx->s_out);
+  plan->last_stream = ctx->stream;
+  if (!rc) rc = bgx_plan_finish(ctx, plan, nullptr);
   if (!rc) {
-    float ms = 0;
-    if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess && kernel_ms) *kernel_ms += ms;
+    double sum = 0;
+    for (uint32_t g = 0; g < G; ++g) {
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, ev[3 * g + 1], ev[3 * g + 2]) == cudaSuccess) sum += ms;
+    }
+    if (kernel_ms) *kernel_ms += sum;
     for (uint32_t i = 0; i < n; ++i) output_sizes[i] = usize[i];
   }
+  for (auto& e : ev) cudaEventDestroy(e);
+  cudaEventDestroy(ev_start);
   bgx_plan_destroy(plan);
   return rc;
 }

@@ -54,7 +54,7 @@ constexpr unsigned kFull = 0xffffffffu;
 constexpr int kCmdLutBits = 9;
 constexpr int kLitLutBits = 10;
 constexpr int kDistLutBits = 9;
-constexpr uint32_t kLitQ = 512;       // literal ring bytes (power of two, multiple of 32)
+constexpr uint32_t kLitQ = 1024;      // literal ring bytes (power of two): two rounds' literals (producer runs one ahead)
 constexpr uint32_t kRing = 2048;      // output ring bytes (power of two, >= kFlushChunk + kRoundMax)
 constexpr uint32_t kRoundMax = 1024;  // largest round (bytes produced) the ring path accepts
 constexpr uint32_t kFlushChunk = 512; // 32 lanes x 16 B
@@ -75,6 +75,19 @@ struct HuffAux {
   uint16_t base[16];    // base[L]  = offset_in_sorted[L] - first_code[L]   (mod 2^16)
 };
 
+struct RoundBuf {            // one round of <= 32 commands, producer -> consumer
+  uint32_t ins[32];
+  uint32_t cpy[32];          // 0 = no copy (insert-only command or no command)
+  uint32_t dx[32];           // explicit distance, or 0x80000000 | short code 0..15 (to be resolved by the consumer)
+};
+struct PageCtl {             // hand-over state of the two warps of a page (read after, written before a barrier)
+  uint32_t produced, consumed;   // rounds published by the producer / retired by the consumer
+  uint32_t slow;                 // 0 none, 1 a slow round was published, 2 consumer is ready for the producer to run it
+  uint32_t pos, lit_head;        // page position / literal index across a slow round
+  uint32_t finished, err, is_delta;
+  uint32_t rflags[2];            // per RoundBuf: bit 0 = last round of the page, bit 1 = slow round
+};
+
 struct WarpSmem {
   uint16_t lut_cmd[1 << kCmdLutBits];
   uint16_t lut_lit[1 << kLitLutBits];
@@ -90,6 +103,8 @@ struct WarpSmem {
   alignas(16) uint8_t ring[kRing];  // output ring; while tables are read: code lengths [0..727] and the
                                     // 512 x u16 code-length-code LUT [1024..2047]
   alignas(16) uint4 stage[4][32];   // compressed-input staging: 4 slots x 16 B per lane (cp.async ring)
+  RoundBuf rb[2];
+  PageCtl ctl;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -187,6 +202,14 @@ BGX_DEV uint32_t br_read(BitRd& r, const PageIn& in, uint32_t n) {   // n <= 32
   const uint32_t v = br_peek(r) & low_mask(n);
   br_skip(r, in, n);
   return v;
+}
+
+BGX_DEV uint32_t warp_index() {
+#ifdef BGX_EMULATED
+  return (uint32_t)wemu::warp_id();
+#else
+  return threadIdx.x >> 5;
+#endif
 }
 
 BGX_DEV uint32_t lane_id() {
@@ -450,431 +473,514 @@ BGX_DEV void decode_literals(WarpSmem* sm, BitRd& rd, const PageIn& in, uint32_t
   }
 }
 
-// The page decoder. All 32 lanes of the warp call it with identical arguments.
-BGX_DEV_NOINLINE PageResult decode_page_warp(const PageJob& job, WarpSmem* sm) {
+// The page decoder: a CTA of TWO warps decodes one page as a two-stage pipeline over rounds.
+//   warp 0, the PRODUCER: owns the 32 bit readers; reads the tables, decodes each round's commands
+//           and literals (everything that consumes bits) and publishes them in a RoundBuf;
+//   warp 1, the CONSUMER: resolves the distance ring, places literals and match copies in the output
+//           ring and streams the page to HBM.
+// One __syncthreads() per iteration hands a round over (double buffered), so the serial dependency
+// chain of a page is split in two halves that run concurrently and the SM holds twice the warps
+// for the same shared-memory footprint. Rounds with long runs ("slow") are executed by the producer
+// straight to global memory after the consumer has resolved their distances and flushed its ring.
+// All threads of the CTA call this with identical arguments.
+BGX_DEV_NOINLINE PageResult decode_page_cta(const PageJob& job, WarpSmem* sm) {
   const uint32_t lane = lane_id();
+  const uint32_t warp = warp_index();
   const uint32_t lt_mask = (1u << lane) - 1u;
+  const uint32_t le_mask = 0xffffffffu >> (31u - lane);
+  PageCtl* ctl = &sm->ctl;
   PageResult res;
   res.status = kPageOk;
   res.is_delta = 0;
-
-  PageIn in;
-  in.base = reinterpret_cast<const uint32_t*>(job.in);
-  in.lim = (job.in_limit >> 2) ? (job.in_limit >> 2) - 1 : 0;
-  {
-    const uintptr_t a = reinterpret_cast<uintptr_t>(job.in);
-    in.g16 = reinterpret_cast<const uint4*>(a & ~(uintptr_t)15);
-    const uint32_t span = (uint32_t)(a & 15u) + job.in_limit;       // bytes readable from g16
-    in.lim16 = (span >> 4) ? (span >> 4) - 1 : 0;
-    in.c0 = 0;
-    in.stage = &sm->stage[0][lane];
-  }
-
-  // ---- length-code tables (RFC 7932 section 5)
-  if (lane < 24) {
-    sm->lenlut[lane] = bgx::insert_base(lane) | (bgx::insert_extra_bits(lane) << 16);
-    sm->lenlut[24 + lane] = bgx::copy_base(lane) | (bgx::copy_extra_bits(lane) << 16);
-  }
-
-  // ---- page header + sub-stream size table (PageDecoder.cpp:79-121): every lane parses the header
-  //      words it needs itself (they are the first few words of the page: broadcast loads)
-  uint32_t npostfix, ndirect, sub_off;
-  {
-    auto hdr_bits = [&](uint32_t pos, uint32_t n) -> uint32_t {   // n <= 25
-      const uint32_t w = pos >> 5, b = pos & 31u;
-      const uint32_t lo = ld_word(in, w), hi = ld_word(in, w + 1);
-      return __funnelshift_r(lo, hi, b) & low_mask(n);
-    };
-    npostfix = hdr_bits(0, 2);
-    ndirect = hdr_bits(2, 4) << npostfix;
-    res.is_delta = hdr_bits(6, 1) && job.allow_delta;
-    const uint32_t base_bits = bgx::floor_log2((job.in_size + 31u) / 32u) + 1u;
-    const uint32_t dbits_bits = bgx::floor_log2(bgx::floor_log2(job.in_size - 1u) + 1u) + 1u;
-    const uint32_t base_size = hdr_bits(8, base_bits);
-    const uint32_t delta_bits = hdr_bits(8 + base_bits, dbits_bits);
-    const uint32_t tbl = 8 + base_bits + dbits_bits;
-    const uint32_t hdr_bytes = ((tbl + 32u * delta_bits + 31u) / 32u) * 4u;
-    const uint32_t dmine = delta_bits ? hdr_bits(tbl + lane * delta_bits, delta_bits > 25 ? 25 : delta_bits) : 0u;
-    const uint32_t mysize = base_size + dmine;
-    sub_off = hdr_bytes + warp_incl_scan(mysize, lane) - mysize;
-  }
-  BitRd rd;
-  br_init(rd, in, sub_off);
-  __syncwarp();
-
-  // ---- the three prefix codes: insert&copy (728), distance (544), literal (256)  (PageDecoder.cpp:126-147)
-  uint32_t terr = load_table<kCmdLutBits>(sm, rd, in, bgx::kNumCmdSymbols, sm->lut_cmd, sm->aux[0], sm->sorted_cmd, lane);
-  if (!terr) terr = load_table<kDistLutBits>(sm, rd, in, bgx::kNumDistSymbols, sm->lut_dist, sm->aux[1], sm->sorted_dist, lane);
-  if (!terr) terr = load_table<kLitLutBits>(sm, rd, in, bgx::kNumLitSymbols, sm->lut_lit, sm->aux[2], sm->sorted_lit, lane);
-  if (terr) { res.status = terr; return res; }
-  __syncwarp();
-
-  // ---- decode state (all uniform across the warp unless noted)
 #ifndef BGX_EMULATED
   __builtin_assume(__isGlobal(job.out));
   __builtin_assume(__isGlobal(job.in));
 #endif
   uint8_t* const out = job.out;
   const uint32_t out_size = job.out_size;
-  const bool out_aligned = (reinterpret_cast<uintptr_t>(out) & 15u) == 0;
+
+  // ---------------- producer state
+  PageIn in;
+  BitRd rd;
+  rd.w0 = rd.w1 = rd.nxt = rd.bitpos = rd.k = 0;
+  uint32_t npostfix = 0, ndirect = 0;
+  uint32_t lit_tail = 0;       // literals decoded so far
+  uint32_t lit_head_p = 0;     // literals that the rounds produced so far consume
+  uint32_t head_prev = 0;      // ... before the most recently produced round (it may still be unconsumed)
+  uint32_t s_ins = 0, s_cpy = 0, s_n = 0, s_mine = 0, s_round_ins = 0;   // a slow round waiting to be executed
+  bool pdone = false;
+  // ---------------- consumer state
   uint32_t pos = 0;            // bytes of the page produced so far
   uint32_t flushed = 0;        // bytes already in global memory
   int32_t ring_from = 0;       // ring holds valid data for positions >= ring_from (and > end - kRing)
-  uint32_t lit_head = 0;       // page-global literal index of the next literal to emit
-  uint32_t lit_tail = 0;       // literals decoded so far
+  uint32_t lit_head = 0;       // page-global literal index of the next literal to place
   uint32_t r0 = 4, r1 = 11, r2 = 15, r3 = 16;   // distance ring (PageDecoder.cpp:150-153)
-  uint32_t err = 0;
-  bool done = false;
+  bool await_slow = false, slow_was_last = false;
+  const bool out_aligned = (reinterpret_cast<uintptr_t>(out) & 15u) == 0;
 
-  while (!done) {
-    // ================= 1. one command per lane, speculatively (lanes after the sentinel roll back)
-    BitRd r = rd;
-    uint32_t len;
-    const uint32_t pk = br_peek(r);
-    uint32_t sym = huff_decode<kCmdLutBits>(sm->lut_cmd, sm->aux[0], sm->sorted_cmd, bgx::kNumCmdSymbols, pk, len);
-    const uint32_t sent = __ballot_sync(kFull, sym == (uint32_t)bgx::kCmdSentinel);
-    const uint32_t n = sent ? (uint32_t)(__ffs((int)sent) - 1) : 32u;   // commands in this round
-    done = sent != 0;
-    uint32_t ins = 0, cpy = 0, dcode = 0, dist = 0;
-    bool has_copy = false;
-    if (lane < n) {
-      uint32_t ic, cc = 0;
-      if (sym < (uint32_t)bgx::kCmdSentinel) {
-        ic = bgx::icp_insert_code(sym);
-        cc = bgx::icp_copy_code(sym);
-        has_copy = true;
-      } else {
-        ic = sym - (uint32_t)bgx::kCmdSentinel;      // insert-only (PageDecoder.cpp:308-317)
-        if (ic > 23u) ic = 23u;
-      }
-      const uint32_t ei = sm->lenlut[ic];
-      const uint32_t ec = has_copy ? sm->lenlut[24 + cc] : 0u;
-      const uint32_t nbi = ei >> 16, nbc = ec >> 16;
-      if (len + nbi + nbc <= 32u) {   // symbol + both extra-bit fields out of the one 32-bit peek
-        ins = (ei & 0xffffu) + (shr32(pk, len) & low_mask(nbi));
-        cpy = (ec & 0xffffu) + (shr32(pk, len + nbi) & low_mask(nbc));
-        br_skip(r, in, len + nbi + nbc);
-      } else {                        // 24-bit extras: field by field
-        br_skip(r, in, len);
-        ins = (ei & 0xffffu) + br_read(r, in, nbi);
-        cpy = (ec & 0xffffu) + br_read(r, in, nbc);
-      }
-      if (has_copy) {
-        if (sym >= 128u) {
-          const uint32_t pk2 = br_peek(r);
-          dcode = huff_decode<kDistLutBits>(sm->lut_dist, sm->aux[1], sm->sorted_dist, bgx::kNumDistSymbols, pk2, len);
-          if (dcode >= 16u + ndirect) {   // explicit distance with extra bits (PageDecoder.cpp:376-394)
-            const uint32_t v = dcode - ndirect - 16u;
-            uint32_t nb = 1u + (v >> (npostfix + 1u));
-            if (nb > 24u) nb = 24u;
-            uint32_t extra;
-            if (len + nb <= 32u) {
-              extra = shr32(pk2, len) & low_mask(nb);
-              br_skip(r, in, len + nb);
-            } else {
-              br_skip(r, in, len);
-              extra = br_read(r, in, nb);
-            }
-            const uint32_t h = v >> npostfix, lo = v & ((1u << npostfix) - 1u);
-            dist = ((((2u + (h & 1u)) << nb) - 4u + extra) << npostfix) + lo + ndirect + 1u;
-          } else {
-            br_skip(r, in, len);
-            if (dcode >= 16u) dist = dcode - 15u;   // direct distance codes (PageDecoder.cpp:369-373)
-          }
-        }
-      }
-      rd = r;
-    } else if (lane == n) {
-      br_skip(r, in, len);
-      rd = r;   // the sentinel's code bits are consumed; its lane then continues with literals
+  if (warp == 0) {
+    if (lane == 0) {
+      ctl->produced = 0; ctl->consumed = 0; ctl->slow = 0; ctl->pos = 0; ctl->lit_head = 0;
+      ctl->finished = 0; ctl->err = 0; ctl->is_delta = 0;
     }
-
-    // ================= 2. positions
-    const uint32_t tot = ins + cpy;
-    const uint64_t incl_both = warp_incl_scan64(((uint64_t)tot << 32) | ins, lane);
-    const uint32_t incl_tot = (uint32_t)(incl_both >> 32);
-    const uint32_t incl_ins = (uint32_t)incl_both;
-    const uint32_t round_out = __shfl_sync(kFull, incl_tot, 31);
-    const uint32_t round_ins = __shfl_sync(kFull, incl_ins, 31);
-    const uint32_t o_ins = pos + incl_tot - tot;        // where this command's literals go
-    const uint32_t o_cpy = o_ins + ins;                 // where its copy goes
-    const uint32_t lq = lit_head + incl_ins - ins;      // page-global index of its first literal
-    if (round_out > out_size - pos) { err = kPageErrOverrun; break; }
-    const uint32_t round_end = pos + round_out;
-
-    // ================= 3. distance ring, resolved by relaxation (PageDecoder.cpp:345-404)
+    in.base = reinterpret_cast<const uint32_t*>(job.in);
+    in.lim = (job.in_limit >> 2) ? (job.in_limit >> 2) - 1 : 0;
     {
-      const uint32_t push = __ballot_sync(kFull, has_copy && dcode != 0);   // commands that enter the ring
-      const uint32_t below = push & lt_mask;
-      bool unresolved = has_copy && dcode < 16u;
-      // which ring slot (0..3) the short code refers to, and the offset applied to it
-      uint32_t slot = 0;
-      int32_t delta = 0;
-      if (unresolved) {
-        if (dcode < 4u) slot = dcode;
-        else {
-          const uint32_t c = dcode - 4u;              // 0..11
-          slot = c >= 6u ? 1u : 0u;
-          const uint32_t k = c >= 6u ? c - 6u : c;    // 0..5 => -1 +1 -2 +2 -3 +3
-          delta = (int32_t)(k >> 1) + 1;
-          if (!(k & 1u)) delta = -delta;
-        }
-      }
-      // source: the slot-th most recent pusher below me, else the carried ring
-      uint32_t b = below;
-      for (uint32_t k = 0; k < slot && b; ++k) b &= ~(1u << (31 - __clz((int)b)));
-      const uint32_t npush_below = __popc(below);
-      const bool from_carry = slot >= npush_below;
-      const uint32_t src_lane = from_carry ? 0u : (uint32_t)(31 - __clz((int)b));
-      const uint32_t cslot = slot - (from_carry ? npush_below : 0u);
-      const uint32_t carry_val = cslot == 0 ? r0 : cslot == 1 ? r1 : cslot == 2 ? r2 : r3;
-      uint32_t resolved = __ballot_sync(kFull, !unresolved);
-      while (resolved != kFull) {
-        BGX_STAT(emu_stats().ring_iters++);
-        const uint32_t v = __shfl_sync(kFull, dist, src_lane);
-        const bool ready = unresolved && (from_carry || ((resolved >> src_lane) & 1u));
-        if (ready) {
-          dist = (uint32_t)((int32_t)(from_carry ? carry_val : v) + delta);
-          unresolved = false;
-        }
-        resolved = __ballot_sync(kFull, !unresolved);
-      }
-      // new carried ring = four most recent pushers of this round, then the old ring
-      uint32_t pb = push;
-      uint32_t nr[4];
-      uint32_t old_idx = 0;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const uint32_t hb = pb ? (uint32_t)(31 - __clz((int)pb)) : 0u;
-        const uint32_t v = __shfl_sync(kFull, dist, hb);
-        if (pb) { nr[k] = v; pb &= ~(1u << hb); }
-        else { nr[k] = old_idx == 0 ? r0 : old_idx == 1 ? r1 : old_idx == 2 ? r2 : r3; ++old_idx; }
-      }
-      r0 = nr[0]; r1 = nr[1]; r2 = nr[2]; r3 = nr[3];
-      const uint32_t baddist = __ballot_sync(kFull, has_copy && (dist == 0 || dist > o_cpy));
-      if (baddist) { err = kPageErrDistance; break; }
+      const uintptr_t a = reinterpret_cast<uintptr_t>(job.in);
+      in.g16 = reinterpret_cast<const uint4*>(a & ~(uintptr_t)15);
+      const uint32_t span = (uint32_t)(a & 15u) + job.in_limit;       // bytes readable from g16
+      in.lim16 = (span >> 4) ? (span >> 4) - 1 : 0;
+      in.c0 = 0;
+      in.stage = &sm->stage[0][lane];
     }
+    // ---- length-code tables (RFC 7932 section 5)
+    if (lane < 24) {
+      sm->lenlut[lane] = bgx::insert_base(lane) | (bgx::insert_extra_bits(lane) << 16);
+      sm->lenlut[24 + lane] = bgx::copy_base(lane) | (bgx::copy_extra_bits(lane) << 16);
+    }
+    // ---- page header + sub-stream size table (PageDecoder.cpp:79-121): every lane parses the header
+    //      words it needs itself (they are the first few words of the page: broadcast loads)
+    uint32_t sub_off;
+    {
+      auto hdr_bits = [&](uint32_t hpos, uint32_t n) -> uint32_t {   // n <= 25
+        const uint32_t w = hpos >> 5, b = hpos & 31u;
+        const uint32_t lo = ld_word(in, w), hi = ld_word(in, w + 1);
+        return __funnelshift_r(lo, hi, b) & low_mask(n);
+      };
+      npostfix = hdr_bits(0, 2);
+      ndirect = hdr_bits(2, 4) << npostfix;
+      const uint32_t is_delta = (hdr_bits(6, 1) && job.allow_delta) ? 1u : 0u;
+      if (lane == 0) ctl->is_delta = is_delta;
+      const uint32_t base_bits = bgx::floor_log2((job.in_size + 31u) / 32u) + 1u;
+      const uint32_t dbits_bits = bgx::floor_log2(bgx::floor_log2(job.in_size - 1u) + 1u) + 1u;
+      const uint32_t base_size = hdr_bits(8, base_bits);
+      const uint32_t delta_bits = hdr_bits(8 + base_bits, dbits_bits);
+      const uint32_t tbl = 8 + base_bits + dbits_bits;
+      const uint32_t hdr_bytes = ((tbl + 32u * delta_bits + 31u) / 32u) * 4u;
+      const uint32_t dmine = delta_bits ? hdr_bits(tbl + lane * delta_bits, delta_bits > 25 ? 25 : delta_bits) : 0u;
+      const uint32_t mysize = base_size + dmine;
+      sub_off = hdr_bytes + warp_incl_scan(mysize, lane) - mysize;
+    }
+    br_init(rd, in, sub_off);
+    __syncwarp();
+    // ---- the three prefix codes: insert&copy (728), distance (544), literal (256)  (PageDecoder.cpp:126-147)
+    uint32_t terr = load_table<kCmdLutBits>(sm, rd, in, bgx::kNumCmdSymbols, sm->lut_cmd, sm->aux[0], sm->sorted_cmd, lane);
+    if (!terr) terr = load_table<kDistLutBits>(sm, rd, in, bgx::kNumDistSymbols, sm->lut_dist, sm->aux[1], sm->sorted_dist, lane);
+    if (!terr) terr = load_table<kLitLutBits>(sm, rd, in, bgx::kNumLitSymbols, sm->lut_lit, sm->aux[2], sm->sorted_lit, lane);
+    if (terr && lane == 0) ctl->err = terr;
+  }
+  __syncthreads();
 
-    // ================= 4. literals of this round (PageDecoder.cpp:196-206)
-    const uint32_t avail = lit_tail - lit_head;     // decoded ahead of need in earlier rounds (< 32)
-    const uint32_t need = round_ins > avail ? round_ins - avail : 0u;
-    const uint32_t mult = n ? (n == 32u ? (need + 31u) >> 5 : (need + n - 1u) / n) : 0u;
-    const uint32_t rl = n * mult;                   // literals the stream carries for this round
-    // lane's share: literal indices lit_tail + j*32 + lane < lit_tail + rl
-    uint32_t mine = rl > lane ? (rl - lane + 31u) >> 5 : 0u;
-    const bool fast = round_out <= kRoundMax && avail + rl <= kLitQ;
+  for (;;) {
+    // snapshot of the hand-over state (written before the last barrier)
+    const uint32_t P = ctl->produced, C = ctl->consumed, S = ctl->slow;
+    const bool stop = ctl->finished || ctl->err;
+    __syncthreads();   // everybody holds the same snapshot before anybody updates it
+    if (stop) break;
 
-    BGX_STAT(emu_stats().rounds++; emu_stats().lits += rl; if (!fast) emu_stats().slow_rounds++);
-    if (fast) {
-#ifdef BGX_STATS
-      {
-        const uint32_t mi = __reduce_max_sync(kFull, ins < kCoopLen ? ins : 0u);
-        const uint32_t ncp = __popc(__ballot_sync(kFull, cpy != 0));
-        const uint32_t far = __reduce_add_sync(kFull, (cpy && dist > 3000u) ? cpy : 0u);
-        const uint32_t ov = __popc(__ballot_sync(kFull, cpy != 0 && dist < cpy));
-        BGX_STAT(emu_stats().sum_max_ins += mi; emu_stats().ins_bytes += round_ins; emu_stats().copies += ncp;
-                 emu_stats().copy_bytes += round_out - round_ins; emu_stats().far_bytes += far; emu_stats().overlap_copies += ov);
-      }
-#endif
-      decode_literals(sm, rd, in, lit_tail, mine, lane);
-      lit_tail += rl;
-      __syncwarp();
-      const int32_t ring_lo = ring_from > (int32_t)round_end - (int32_t)kRing ? ring_from : (int32_t)round_end - (int32_t)kRing;
-
-      // ---- 5. inserts, flattened: lane t places literal t of the round (perfectly balanced, any length).
-      //         Commands with literals are compacted into tab[]; a per-chunk bit mask of their first
-      //         literal index turns "which command owns literal t" into one popc.
-      uint32_t* tab = sm->scratch;                       // [32] (o_ins - first literal index)
-      uint4* tab2 = reinterpret_cast<uint4*>(sm->scratch + 32);   // [32] (dst - first flat index, distance, dst start)
-      const uint32_t le_mask = 0xffffffffu >> (31u - lane);
-      {
-        const uint32_t has = __ballot_sync(kFull, ins != 0);
-        const uint32_t S = incl_ins - ins;               // round-local index of this command's first literal
-        if (ins) tab[__popc(has & lt_mask)] = o_ins - S;
-        __syncwarp();
-        uint32_t before = 0;
-        for (uint32_t c0 = 0; c0 < round_ins; c0 += 32) {
-          const uint32_t M = __reduce_or_sync(kFull, (ins && S - c0 < 32u) ? (1u << (S - c0)) : 0u);
-          const uint32_t t = c0 + lane;
-          if (t < round_ins) {
-            const uint32_t ord = before + __popc(M & le_mask) - 1u;
-            sm->ring[(tab[ord] + t) & (kRing - 1)] = sm->litq[(lit_head + t) & (kLitQ - 1)];
+    if (warp == 0) {
+      // =============================================================== PRODUCER
+      if (S == 0 && !pdone && P - C < 2u) {
+        RoundBuf* rb = &sm->rb[P & 1u];
+        // ---- one command per lane, speculatively (lanes after the sentinel roll back)
+        BitRd r = rd;
+        uint32_t len;
+        const uint32_t pk = br_peek(r);
+        uint32_t sym = huff_decode<kCmdLutBits>(sm->lut_cmd, sm->aux[0], sm->sorted_cmd, bgx::kNumCmdSymbols, pk, len);
+        const uint32_t sent = __ballot_sync(kFull, sym == (uint32_t)bgx::kCmdSentinel);
+        const uint32_t n = sent ? (uint32_t)(__ffs((int)sent) - 1) : 32u;   // commands in this round
+        pdone = sent != 0;
+        uint32_t ins = 0, cpy = 0, dx = 0;   // dx: explicit distance, or 0x80000000 | short code 0..15
+        if (lane < n) {
+          uint32_t ic, cc = 0;
+          bool has_copy = false;
+          if (sym < (uint32_t)bgx::kCmdSentinel) {
+            ic = bgx::icp_insert_code(sym);
+            cc = bgx::icp_copy_code(sym);
+            has_copy = true;
+          } else {
+            ic = sym - (uint32_t)bgx::kCmdSentinel;      // insert-only (PageDecoder.cpp:308-317)
+            if (ic > 23u) ic = 23u;
           }
-          before += __popc(M);
-        }
-      }
-      __syncwarp();
-
-      // ---- 6. copies. Wavefront 1 (flattened, like the inserts): every copy whose source already is
-      //         final -- it lies below the destination of the first pending copy -- and that does not
-      //         overlap its own destination. Sources may be in the ring or (far matches) in L1/L2.
-      const uint32_t src_lo = o_cpy - dist;                              // first source byte
-      const uint32_t src_hi = src_lo + (cpy < dist ? cpy : dist);        // one past the last distinct source byte
-      uint32_t pending = __ballot_sync(kFull, cpy != 0);
-      if (pending) {
-        const int first = __ffs((int)pending) - 1;
-        const uint32_t hwm = __shfl_sync(kFull, o_cpy, first);           // everything below is final
-        const bool ready1 = cpy != 0 && ((int)lane == first || src_hi <= hwm);
-        const uint32_t len1 = ready1 ? cpy : 0u;
-        const uint32_t E1 = warp_incl_scan(len1, lane);
-        const uint32_t T1 = __shfl_sync(kFull, E1, 31);
-        const uint32_t S1 = E1 - len1;
-        const uint32_t m1 = __ballot_sync(kFull, ready1);
-        if (ready1) tab2[__popc(m1 & lt_mask)] = make_uint4(o_cpy - S1, dist, o_cpy, 0u);
-        __syncwarp();
-        uint32_t before = 0;
-        for (uint32_t c0 = 0; c0 < T1; c0 += 128) {      // four 32-byte chunks per trip: all loads go out before the stores
-          uint32_t d[4];
-          uint8_t v[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const uint32_t cu = c0 + 32u * u;
-            const uint32_t M = __reduce_or_sync(kFull, (ready1 && S1 - cu < 32u) ? (1u << (S1 - cu)) : 0u);
-            const uint32_t t = cu + lane;
-            d[u] = 0xffffffffu;
-            v[u] = 0;
-            if (t < T1) {
-              const uint4 p = tab2[before + __popc(M & le_mask) - 1u];
-              d[u] = p.x + t;
-              uint32_t j = d[u] - p.z;            // byte index inside the copy
-              if (j >= p.y) j %= p.y;             // overlapping copy: pattern of `dist` bytes repeats (PageDecoder.cpp:222-232)
-              v[u] = out_byte(sm, out, ring_lo, p.z - p.y + j);
+          const uint32_t ei = sm->lenlut[ic];
+          const uint32_t ec = has_copy ? sm->lenlut[24 + cc] : 0u;
+          const uint32_t nbi = ei >> 16, nbc = ec >> 16;
+          if (len + nbi + nbc <= 32u) {   // symbol + both extra-bit fields out of the one 32-bit peek
+            ins = (ei & 0xffffu) + (shr32(pk, len) & low_mask(nbi));
+            cpy = (ec & 0xffffu) + (shr32(pk, len + nbi) & low_mask(nbc));
+            br_skip(r, in, len + nbi + nbc);
+          } else {                        // 24-bit extras: field by field
+            br_skip(r, in, len);
+            ins = (ei & 0xffffu) + br_read(r, in, nbi);
+            cpy = (ec & 0xffffu) + br_read(r, in, nbc);
+          }
+          if (has_copy) {
+            dx = 0x80000000u;             // implicit "last distance" (symbol < 128, PageDecoder.cpp:305)
+            if (sym >= 128u) {
+              const uint32_t pk2 = br_peek(r);
+              const uint32_t dcode = huff_decode<kDistLutBits>(sm->lut_dist, sm->aux[1], sm->sorted_dist, bgx::kNumDistSymbols, pk2, len);
+              if (dcode >= 16u + ndirect) {   // explicit distance with extra bits (PageDecoder.cpp:376-394)
+                const uint32_t v = dcode - ndirect - 16u;
+                uint32_t nb = 1u + (v >> (npostfix + 1u));
+                if (nb > 24u) nb = 24u;
+                uint32_t extra;
+                if (len + nb <= 32u) {
+                  extra = shr32(pk2, len) & low_mask(nb);
+                  br_skip(r, in, len + nb);
+                } else {
+                  br_skip(r, in, len);
+                  extra = br_read(r, in, nb);
+                }
+                const uint32_t h = v >> npostfix, lo = v & ((1u << npostfix) - 1u);
+                dx = (((((2u + (h & 1u)) << nb) - 4u + extra) << npostfix) + lo + ndirect + 1u) & 0x7fffffffu;
+              } else {
+                br_skip(r, in, len);
+                dx = dcode >= 16u ? dcode - 15u : (0x80000000u | dcode);   // direct codes (PageDecoder.cpp:369-373) / ring codes
+              }
             }
-            before += __popc(M);
+          } else {
+            cpy = 0;
           }
-#pragma unroll
-          for (int u = 0; u < 4; ++u)
-            if (d[u] != 0xffffffffu) sm->ring[d[u] & (kRing - 1)] = v[u];
+          rd = r;
+        } else if (lane == n) {
+          br_skip(r, in, len);
+          rd = r;   // the sentinel's code bits are consumed; its lane then continues with literals
         }
-        __syncwarp();
-        pending &= ~m1;
-      }
-      //         Remaining copies (dependent on this round's copies, or overlapping themselves): in
-      //         wavefronts, one lane per command, byte-serial.
-      while (pending) {
-        const int first = __ffs((int)pending) - 1;
-        const uint32_t hwm = __shfl_sync(kFull, o_cpy, first);
-        const bool ready = ((pending >> lane) & 1u) && ((int)lane == first || src_hi <= hwm);
-#ifdef BGX_STATS
-        {
-          const uint32_t mc = __reduce_max_sync(kFull, (ready && cpy < kCoopLen) ? cpy : 0u);
-          const uint32_t nc = __popc(__ballot_sync(kFull, ready && cpy >= kCoopLen));
-          BGX_STAT(emu_stats().wavefronts++; emu_stats().sum_max_cpy += mc; emu_stats().coop_copies += nc);
+        rb->ins[lane] = ins;
+        rb->cpy[lane] = cpy;
+        rb->dx[lane] = dx;
+        // ---- literals of this round (PageDecoder.cpp:196-206)
+        const uint32_t round_ins = __reduce_add_sync(kFull, ins);
+        const uint32_t round_out = round_ins + __reduce_add_sync(kFull, cpy);
+        const uint32_t avail = lit_tail - lit_head_p;     // decoded ahead of need in earlier rounds (< 32)
+        const uint32_t need = round_ins > avail ? round_ins - avail : 0u;
+        const uint32_t mult = n ? (n == 32u ? (need + 31u) >> 5 : (need + n - 1u) / n) : 0u;
+        const uint32_t rl = n * mult;                     // literals the stream carries for this round
+        const uint32_t mine = rl > lane ? (rl - lane + 31u) >> 5 : 0u;   // literal indices lit_tail + j*32 + lane
+        // the literal ring must hold this round's literals next to those of the round the consumer still works on
+        const bool fast = round_out <= kRoundMax && (lit_tail - head_prev) + rl <= kLitQ;
+        BGX_STAT(emu_stats().rounds++; emu_stats().lits += rl; if (!fast) emu_stats().slow_rounds++);
+        if (fast) {
+          decode_literals(sm, rd, in, lit_tail, mine, lane);
+          lit_tail += rl;
+          head_prev = lit_head_p;
+          lit_head_p += round_ins;
+        } else {
+          s_ins = ins; s_cpy = cpy; s_n = n; s_mine = mine; s_round_ins = round_ins;
         }
-#endif
-        if (ready && cpy < kCoopLen) {
-          // byte-serial, so an overlapping copy (dist < len) replicates its pattern exactly as
-          // PageDecoder.cpp:222-232 does: later bytes read what this loop has just written
-          for (uint32_t j = 0; j < cpy; ++j)
-            sm->ring[(o_cpy + j) & (kRing - 1)] = out_byte(sm, out, ring_lo, src_lo + j);
+        if (lane == 0) {
+          ctl->rflags[P & 1u] = (pdone ? 1u : 0u) | (fast ? 0u : 2u);
+          ctl->produced = P + 1u;
+          if (!fast) ctl->slow = 1u;
         }
-        const uint32_t ready_mask = __ballot_sync(kFull, ready);
-        uint32_t bigc = __ballot_sync(kFull, ready && cpy >= kCoopLen);
-        __syncwarp();
-        while (bigc) {
-          const int k = __ffs((int)bigc) - 1;
-          bigc &= bigc - 1;
-          const uint32_t n_k = __shfl_sync(kFull, cpy, k);
-          const uint32_t o_k = __shfl_sync(kFull, o_cpy, k);
-          const uint32_t d_k = __shfl_sync(kFull, dist, k);
-          const uint32_t s_k = o_k - d_k;
-          // byte j of the copy = pattern byte (j mod dist) of the dist bytes preceding the destination
-          for (uint32_t j = lane; j < n_k; j += 32) {
-            const uint32_t m = j < d_k ? j : j % d_k;
-            sm->ring[(o_k + j) & (kRing - 1)] = out_byte(sm, out, ring_lo, s_k + m);
+      } else if (S == 2u) {
+        // ---- execute the slow round (long runs) straight to global memory, command by command.
+        //      The consumer has resolved the distances (rb->dx), flushed its ring and published pos.
+        RoundBuf* rb = &sm->rb[C & 1u];
+        uint32_t p = ctl->pos;
+        uint32_t lh = lit_head_p;
+        uint32_t err = 0;
+        for (uint32_t k = 0; k < s_n; ++k) {
+          uint32_t n_ins = __shfl_sync(kFull, s_ins, (int)k);
+          const uint32_t n_cpy = __shfl_sync(kFull, s_cpy, (int)k);
+          const uint32_t d_k = rb->dx[k];
+          while (n_ins) {
+            uint32_t have = lit_tail - lh;
+            if (have == 0) {
+              // decode the next chunk of this round's literals (as many as the literal ring takes)
+              const uint32_t room = kLitQ >> 5;
+              const uint32_t c = s_mine < room ? s_mine : room;
+              const uint32_t total = __reduce_add_sync(kFull, c);
+              if (total == 0) { err = kPageErrLiterals; break; }
+              decode_literals(sm, rd, in, lit_tail, c, lane);
+              s_mine -= c;
+              lit_tail += total;
+              __syncwarp();
+              have = lit_tail - lh;
+            }
+            const uint32_t take = n_ins < have ? n_ins : have;
+            for (uint32_t j = lane; j < take; j += 32) out[p + j] = sm->litq[(lh + j) & (kLitQ - 1)];
+            p += take;
+            lh += take;
+            n_ins -= take;
+            __syncwarp();
           }
+          if (err) break;
+          if (n_cpy) {
+            const uint32_t s_k = p - d_k;
+            for (uint32_t j = lane; j < n_cpy; j += 32) {
+              const uint32_t m = j < d_k ? j : j % d_k;
+              out[p + j] = out[s_k + m];
+            }
+            p += n_cpy;
+            __syncwarp();
+          }
+        }
+        // literals the round still carries (decoded ahead of need, at most 31 remain unused)
+        while (!err && __reduce_add_sync(kFull, s_mine) != 0) {
+          const uint32_t room = (kLitQ - (lit_tail - lh)) >> 5;
+          const uint32_t c = s_mine < room ? s_mine : room;
+          const uint32_t total = __reduce_add_sync(kFull, c);
+          if (total == 0) { err = kPageErrLiterals; break; }
+          decode_literals(sm, rd, in, lit_tail, c, lane);
+          s_mine -= c;
+          lit_tail += total;
           __syncwarp();
         }
-        pending &= ~ready_mask;
-      }
-      pos = round_end;
-      lit_head += round_ins;
-      // ---- 7. write-combined flush of complete 512-byte chunks
-      if (pos - flushed >= kFlushChunk) {
-        if (out_aligned) {
-          if (flushed & 15u) {   // after a cooperative (direct) episode the flush point may be unaligned
-            const uint32_t to = (flushed + 15u) & ~15u;
-            flush_bytes(sm, out, flushed, to, lane);
-            flushed = to;
-          }
-          while (pos - flushed >= kFlushChunk) {
-            const uint32_t p = flushed + 16u * lane;
-            *reinterpret_cast<uint4*>(out + p) = *reinterpret_cast<const uint4*>(&sm->ring[p & (kRing - 1)]);
-            flushed += kFlushChunk;
-          }
-        } else {
-          const uint32_t to = flushed + ((pos - flushed) / kFlushChunk) * kFlushChunk;
-          flush_bytes(sm, out, flushed, to, lane);
-          flushed = to;
+        lit_head_p = lh;
+        head_prev = lh;
+        if (lane == 0) {
+          ctl->pos = p;
+          ctl->lit_head = lh;
+          ctl->consumed = C + 1u;
+          ctl->slow = 0u;
+          if (err) ctl->err = err;
         }
-        __syncwarp();
       }
     } else {
-      // ================= slow path: long runs, straight to global memory, command by command
-      flush_bytes(sm, out, flushed, pos, lane);
-      flushed = pos;
-      __syncwarp();
-      for (uint32_t k = 0; k < n; ++k) {
-        uint32_t n_ins = __shfl_sync(kFull, ins, (int)k);
-        const uint32_t n_cpy = __shfl_sync(kFull, cpy, (int)k);
-        const uint32_t d_k = __shfl_sync(kFull, dist, (int)k);
-        while (n_ins) {
-          uint32_t have = lit_tail - lit_head;
-          if (have == 0) {
-            // decode the next chunk of this round's literals (as many as the literal ring takes)
-            const uint32_t room = (kLitQ - have) >> 5;
-            const uint32_t c = mine < room ? mine : room;
-            const uint32_t total = __reduce_add_sync(kFull, c);
-            if (total == 0) { err = kPageErrLiterals; break; }
-            decode_literals(sm, rd, in, lit_tail, c, lane);
-            mine -= c;
-            lit_tail += total;
+      // =============================================================== CONSUMER
+      if (await_slow && S == 0u) {            // the producer has executed the slow round: pick the page up again
+        pos = ctl->pos;
+        flushed = pos;
+        ring_from = (int32_t)pos;
+        lit_head = ctl->lit_head;
+        await_slow = false;
+        if (slow_was_last) {
+          for (uint32_t q = pos + lane; q < out_size; q += 32) out[q] = 0;
+          if (lane == 0) ctl->finished = 1u;
+        }
+      } else if (S != 2u && C < P && !await_slow) {
+        RoundBuf* rb = &sm->rb[C & 1u];
+        const uint32_t rflags = ctl->rflags[C & 1u];
+        const uint32_t ins = rb->ins[lane], cpy = rb->cpy[lane], dx = rb->dx[lane];
+        const bool has_copy = cpy != 0;
+        const uint32_t dcode = (dx >> 31) ? (dx & 0xffu) : 16u;   // 16 = explicit distance
+        uint32_t dist = (dx >> 31) ? 0u : dx;
+        uint32_t err = 0;
+        // ---- positions
+        const uint32_t tot = ins + cpy;
+        const uint64_t incl_both = warp_incl_scan64(((uint64_t)tot << 32) | ins, lane);
+        const uint32_t incl_tot = (uint32_t)(incl_both >> 32);
+        const uint32_t incl_ins = (uint32_t)incl_both;
+        const uint32_t round_out = __shfl_sync(kFull, incl_tot, 31);
+        const uint32_t round_ins = __shfl_sync(kFull, incl_ins, 31);
+        const uint32_t o_ins = pos + incl_tot - tot;        // where this command's literals go
+        const uint32_t o_cpy = o_ins + ins;                 // where its copy goes
+        if (round_out > out_size - pos) err = kPageErrOverrun;
+        const uint32_t round_end = pos + round_out;
+        // ---- distance ring, resolved by relaxation (PageDecoder.cpp:345-404)
+        {
+          const uint32_t push = __ballot_sync(kFull, has_copy && dcode != 0);   // commands that enter the ring
+          const uint32_t below = push & lt_mask;
+          bool unresolved = has_copy && dcode < 16u;
+          uint32_t slot = 0;       // which ring slot (0..3) the short code refers to, and the offset applied to it
+          int32_t delta = 0;
+          if (unresolved) {
+            if (dcode < 4u) slot = dcode;
+            else {
+              const uint32_t c = dcode - 4u;              // 0..11
+              slot = c >= 6u ? 1u : 0u;
+              const uint32_t k = c >= 6u ? c - 6u : c;    // 0..5 => -1 +1 -2 +2 -3 +3
+              delta = (int32_t)(k >> 1) + 1;
+              if (!(k & 1u)) delta = -delta;
+            }
+          }
+          // source: the slot-th most recent pusher below me, else the carried ring
+          uint32_t b = below;
+          for (uint32_t k = 0; k < slot && b; ++k) b &= ~(1u << (31 - __clz((int)b)));
+          const uint32_t npush_below = __popc(below);
+          const bool from_carry = slot >= npush_below;
+          const uint32_t src_lane = from_carry ? 0u : (uint32_t)(31 - __clz((int)b));
+          const uint32_t cslot = slot - (from_carry ? npush_below : 0u);
+          const uint32_t carry_val = cslot == 0 ? r0 : cslot == 1 ? r1 : cslot == 2 ? r2 : r3;
+          uint32_t resolved = __ballot_sync(kFull, !unresolved);
+          while (resolved != kFull) {
+            BGX_STAT(emu_stats().ring_iters++);
+            const uint32_t v = __shfl_sync(kFull, dist, src_lane);
+            const bool ready = unresolved && (from_carry || ((resolved >> src_lane) & 1u));
+            if (ready) {
+              dist = (uint32_t)((int32_t)(from_carry ? carry_val : v) + delta);
+              unresolved = false;
+            }
+            resolved = __ballot_sync(kFull, !unresolved);
+          }
+          if (push) {   // new carried ring = four most recent pushers of this round, then the old ring
+            uint32_t pb = push;
+            uint32_t nr[4];
+            uint32_t old_idx = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint32_t hb = pb ? (uint32_t)(31 - __clz((int)pb)) : 0u;
+              const uint32_t v = __shfl_sync(kFull, dist, hb);
+              if (pb) { nr[k] = v; pb &= ~(1u << hb); }
+              else { nr[k] = old_idx == 0 ? r0 : old_idx == 1 ? r1 : old_idx == 2 ? r2 : r3; ++old_idx; }
+            }
+            r0 = nr[0]; r1 = nr[1]; r2 = nr[2]; r3 = nr[3];
+          }
+          const uint32_t baddist = __ballot_sync(kFull, has_copy && (dist == 0 || dist > o_cpy));
+          if (baddist && !err) err = kPageErrDistance;
+        }
+        if (err) {
+          if (lane == 0) ctl->err = err;
+        } else if (rflags & 2u) {
+          // ---- slow round: hand the resolved distances and a fully flushed page over to the producer
+          rb->dx[lane] = dist;
+          flush_bytes(sm, out, flushed, pos, lane);
+          flushed = pos;
+          await_slow = true;
+          slow_was_last = (rflags & 1u) != 0;
+          if (lane == 0) { ctl->pos = pos; ctl->slow = 2u; }
+        } else {
+          const uint32_t lq = incl_ins - ins;                // round-local index of this command's first literal
+          const int32_t ring_lo = ring_from > (int32_t)round_end - (int32_t)kRing ? ring_from : (int32_t)round_end - (int32_t)kRing;
+#ifdef BGX_STATS
+          {
+            const uint32_t mi = __reduce_max_sync(kFull, ins < kCoopLen ? ins : 0u);
+            const uint32_t ncp = __popc(__ballot_sync(kFull, cpy != 0));
+            const uint32_t far = __reduce_add_sync(kFull, (cpy && dist > 1500u) ? cpy : 0u);
+            const uint32_t ov = __popc(__ballot_sync(kFull, cpy != 0 && dist < cpy));
+            BGX_STAT(emu_stats().sum_max_ins += mi; emu_stats().ins_bytes += round_ins; emu_stats().copies += ncp;
+                     emu_stats().copy_bytes += round_out - round_ins; emu_stats().far_bytes += far; emu_stats().overlap_copies += ov);
+          }
+#endif
+          // ---- inserts, flattened: lane t places literal t of the round (perfectly balanced, any length).
+          //      Commands with literals are compacted into tab[]; a per-chunk bit mask of their first
+          //      literal index turns "which command owns literal t" into one popc.
+          uint32_t* tab = sm->scratch;                       // [32] (o_ins - first literal index)
+          uint4* tab2 = reinterpret_cast<uint4*>(sm->scratch + 32);   // [32] (dst - first flat index, distance, dst start)
+          {
+            const uint32_t has = __ballot_sync(kFull, ins != 0);
+            if (ins) tab[__popc(has & lt_mask)] = o_ins - lq;
             __syncwarp();
-            have = lit_tail - lit_head;
+            uint32_t before = 0;
+            for (uint32_t c0 = 0; c0 < round_ins; c0 += 32) {
+              const uint32_t M = __reduce_or_sync(kFull, (ins && lq - c0 < 32u) ? (1u << (lq - c0)) : 0u);
+              const uint32_t t = c0 + lane;
+              if (t < round_ins) {
+                const uint32_t ord = before + __popc(M & le_mask) - 1u;
+                sm->ring[(tab[ord] + t) & (kRing - 1)] = sm->litq[(lit_head + t) & (kLitQ - 1)];
+              }
+              before += __popc(M);
+            }
           }
-          const uint32_t take = n_ins < have ? n_ins : have;
-          for (uint32_t j = lane; j < take; j += 32) out[pos + j] = sm->litq[(lit_head + j) & (kLitQ - 1)];
-          pos += take;
-          lit_head += take;
-          n_ins -= take;
           __syncwarp();
-        }
-        if (err) break;
-        if (n_cpy) {
-          const uint32_t s_k = pos - d_k;
-          for (uint32_t j = lane; j < n_cpy; j += 32) {
-            const uint32_t m = j < d_k ? j : j % d_k;
-            out[pos + j] = out[s_k + m];
+          // ---- copies. Wavefront 1 (flattened, like the inserts): every copy whose source already is
+          //      final, i.e. lies below the destination of the first pending copy. Sources may be in
+          //      the ring or (far matches) in L1/L2.
+          const uint32_t src_lo = o_cpy - dist;                              // first source byte
+          const uint32_t src_hi = src_lo + (cpy < dist ? cpy : dist);        // one past the last distinct source byte
+          uint32_t pending = __ballot_sync(kFull, cpy != 0);
+          if (pending) {
+            const int first = __ffs((int)pending) - 1;
+            const uint32_t hwm = __shfl_sync(kFull, o_cpy, first);           // everything below is final
+            const bool ready1 = cpy != 0 && ((int)lane == first || src_hi <= hwm);
+            const uint32_t len1 = ready1 ? cpy : 0u;
+            const uint32_t E1 = warp_incl_scan(len1, lane);
+            const uint32_t T1 = __shfl_sync(kFull, E1, 31);
+            const uint32_t S1 = E1 - len1;
+            const uint32_t m1 = __ballot_sync(kFull, ready1);
+            if (ready1) tab2[__popc(m1 & lt_mask)] = make_uint4(o_cpy - S1, dist, o_cpy, 0u);
+            __syncwarp();
+            uint32_t before = 0;
+            for (uint32_t c0 = 0; c0 < T1; c0 += 128) {      // four 32-byte chunks per trip: all loads go out before the stores
+              uint32_t d[4];
+              uint8_t v[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const uint32_t cu = c0 + 32u * u;
+                const uint32_t M = __reduce_or_sync(kFull, (ready1 && S1 - cu < 32u) ? (1u << (S1 - cu)) : 0u);
+                const uint32_t t = cu + lane;
+                d[u] = 0xffffffffu;
+                v[u] = 0;
+                if (t < T1) {
+                  const uint4 q = tab2[before + __popc(M & le_mask) - 1u];
+                  d[u] = q.x + t;
+                  uint32_t j = d[u] - q.z;            // byte index inside the copy
+                  if (j >= q.y) j %= q.y;             // overlapping copy: pattern of `dist` bytes repeats (PageDecoder.cpp:222-232)
+                  v[u] = out_byte(sm, out, ring_lo, q.z - q.y + j);
+                }
+                before += __popc(M);
+              }
+#pragma unroll
+              for (int u = 0; u < 4; ++u)
+                if (d[u] != 0xffffffffu) sm->ring[d[u] & (kRing - 1)] = v[u];
+            }
+            __syncwarp();
+            pending &= ~m1;
           }
-          pos += n_cpy;
-          __syncwarp();
+          //      Remaining copies (dependent on this round's copies): in wavefronts, one lane per
+          //      command, byte-serial (exact overlap semantics); long ones by the whole warp.
+          while (pending) {
+            const int first = __ffs((int)pending) - 1;
+            const uint32_t hwm = __shfl_sync(kFull, o_cpy, first);
+            const bool ready = ((pending >> lane) & 1u) && ((int)lane == first || src_hi <= hwm);
+#ifdef BGX_STATS
+            {
+              const uint32_t mc = __reduce_max_sync(kFull, (ready && cpy < kCoopLen) ? cpy : 0u);
+              const uint32_t nc = __popc(__ballot_sync(kFull, ready && cpy >= kCoopLen));
+              BGX_STAT(emu_stats().wavefronts++; emu_stats().sum_max_cpy += mc; emu_stats().coop_copies += nc);
+            }
+#endif
+            if (ready && cpy < kCoopLen) {
+              for (uint32_t j = 0; j < cpy; ++j)
+                sm->ring[(o_cpy + j) & (kRing - 1)] = out_byte(sm, out, ring_lo, src_lo + j);
+            }
+            const uint32_t ready_mask = __ballot_sync(kFull, ready);
+            uint32_t bigc = __ballot_sync(kFull, ready && cpy >= kCoopLen);
+            __syncwarp();
+            while (bigc) {
+              const int k = __ffs((int)bigc) - 1;
+              bigc &= bigc - 1;
+              const uint32_t n_k = __shfl_sync(kFull, cpy, k);
+              const uint32_t o_k = __shfl_sync(kFull, o_cpy, k);
+              const uint32_t d_k = __shfl_sync(kFull, dist, k);
+              const uint32_t s_k = o_k - d_k;
+              // byte j of the copy = pattern byte (j mod dist) of the dist bytes preceding the destination
+              for (uint32_t j = lane; j < n_k; j += 32) {
+                const uint32_t m = j < d_k ? j : j % d_k;
+                sm->ring[(o_k + j) & (kRing - 1)] = out_byte(sm, out, ring_lo, s_k + m);
+              }
+              __syncwarp();
+            }
+            pending &= ~ready_mask;
+          }
+          pos = round_end;
+          lit_head += round_ins;
+          // ---- write-combined flush of complete 512-byte chunks
+          if (pos - flushed >= kFlushChunk) {
+            if (out_aligned) {
+              if (flushed & 15u) {   // after a cooperative (direct) episode the flush point may be unaligned
+                const uint32_t to = (flushed + 15u) & ~15u;
+                flush_bytes(sm, out, flushed, to, lane);
+                flushed = to;
+              }
+              while (pos - flushed >= kFlushChunk) {
+                const uint32_t q = flushed + 16u * lane;
+                *reinterpret_cast<uint4*>(out + q) = *reinterpret_cast<const uint4*>(&sm->ring[q & (kRing - 1)]);
+                flushed += kFlushChunk;
+              }
+            } else {
+              const uint32_t to = flushed + ((pos - flushed) / kFlushChunk) * kFlushChunk;
+              flush_bytes(sm, out, flushed, to, lane);
+              flushed = to;
+            }
+            __syncwarp();
+          }
+          if (rflags & 1u) {
+            // ---- last round: whatever is still only in the ring, then zero-fill (the reference memsets the page first)
+            flush_bytes(sm, out, flushed, pos, lane);
+            for (uint32_t q = pos + lane; q < out_size; q += 32) out[q] = 0;
+            if (lane == 0) ctl->finished = 1u;
+          }
+          if (lane == 0) ctl->consumed = C + 1u;
         }
       }
-      if (err) break;
-      // literals the round still carries (decoded ahead of need, at most 31 remain unused)
-      while (__reduce_add_sync(kFull, mine) != 0) {
-        const uint32_t room = (kLitQ - (lit_tail - lit_head)) >> 5;
-        const uint32_t c = mine < room ? mine : room;
-        const uint32_t total = __reduce_add_sync(kFull, c);
-        if (total == 0) { err = kPageErrLiterals; break; }
-        decode_literals(sm, rd, in, lit_tail, c, lane);
-        mine -= c;
-        lit_tail += total;
-        __syncwarp();
-      }
-      if (err) break;
-      flushed = pos;
-      ring_from = (int32_t)pos;
     }
+    __syncthreads();
   }
-
-  // ---- tail: whatever is still only in the ring, then zero-fill (reference memsets the page first)
-  if (!err) {
-    flush_bytes(sm, out, flushed, pos, lane);
-    for (uint32_t p = pos + lane; p < out_size; p += 32) out[p] = 0;
-  }
-  __syncwarp();
-  res.status = err;
+  res.status = ctl->err;
+  res.is_delta = ctl->is_delta;
+  __syncthreads();     // everybody has read the result before the page arena is reused
   return res;
 }
 
@@ -967,30 +1073,22 @@ BGX_DEV void copy_page_warp(uint8_t* dst, const uint8_t* src, uint32_t n) {
     }
     for (; v < nv; v += 32) d[v] = s[v];
     i = nv << 4;
-  } else if (((a & 15u) == 0) && ((b & 7u) == 0)) {
-    // typical stream layout: page data sits 8 bytes off a 16-byte boundary (8-byte header + 4n-byte table)
+  } else if (((a | b) & 7u) == 0) {
+    // typical stream layout: page data sits 8 bytes off a 16-byte boundary (8-byte header + 4n-byte table):
+    // copy in coalesced 8-byte units, 8 loads in flight per lane
     const uint2* s = reinterpret_cast<const uint2*>(src);
-    uint4* d = reinterpret_cast<uint4*>(dst);
-    const uint32_t nv = n >> 4;
+    uint2* d = reinterpret_cast<uint2*>(dst);
+    const uint32_t nv = n >> 3;
     uint32_t v = lane;
     for (; v + 7 * 32 < nv; v += 8 * 32) {
-      uint2 t[16];
+      uint2 t[8];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) { t[2 * u] = s[2 * (v + u * 32)]; t[2 * u + 1] = s[2 * (v + u * 32) + 1]; }
+      for (int u = 0; u < 8; ++u) t[u] = s[v + u * 32];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        uint4 w;
-        w.x = t[2 * u].x; w.y = t[2 * u].y; w.z = t[2 * u + 1].x; w.w = t[2 * u + 1].y;
-        d[v + u * 32] = w;
-      }
+      for (int u = 0; u < 8; ++u) d[v + u * 32] = t[u];
     }
-    for (; v < nv; v += 32) {
-      const uint2 lo = s[2 * v], hi = s[2 * v + 1];
-      uint4 w;
-      w.x = lo.x; w.y = lo.y; w.z = hi.x; w.w = hi.y;
-      d[v] = w;
-    }
-    i = nv << 4;
+    for (; v < nv; v += 32) d[v] = s[v];
+    i = nv << 3;
   } else if (((a | b) & 3u) == 0) {
     const uint32_t* s = reinterpret_cast<const uint32_t*>(src);
     uint32_t* d = reinterpret_cast<uint32_t*>(dst);
@@ -1007,6 +1105,14 @@ BGX_DEV void copy_page_warp(uint8_t* dst, const uint8_t* src, uint32_t n) {
     i = nv << 2;
   }
   for (uint32_t j = i + lane; j < n; j += 32) dst[j] = src[j];
+}
+
+// both warps of the page's CTA take half of a raw page each
+BGX_DEV void copy_page_cta(uint8_t* dst, const uint8_t* src, uint32_t n) {
+  uint32_t h = ((n >> 1) + 255u) & ~255u;
+  if (h > n) h = n;
+  if (warp_index() == 0) copy_page_warp(dst, src, h);
+  else copy_page_warp(dst + h, src + h, n - h);
 }
 
 }  // namespace bgxk

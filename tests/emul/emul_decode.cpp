@@ -53,7 +53,7 @@ int emul_decode_stream(const uint8_t* src, uint32_t src_size, uint8_t* dst, uint
     const bgx::PageExtent e = bgx::page_extent(si, table, p);
     bgxk::PageResult res{0, 0};
     if (e.in_size == e.out_size) {
-      coll += wemu::run_warp([&] { bgxk::copy_page_warp(dst + e.out_off, pages + e.in_off, e.out_size); });
+      coll += wemu::run_block(2, [&] { bgxk::copy_page_cta(dst + e.out_off, pages + e.in_off, e.out_size); });
     } else {
       bgxk::PageJob job;
       job.in = pages + e.in_off;
@@ -62,10 +62,10 @@ int emul_decode_stream(const uint8_t* src, uint32_t src_size, uint8_t* dst, uint
       job.out = dst + e.out_off;
       job.out_size = e.out_size;
       job.allow_delta = si.preconditioned;
-      bgxk::PageResult results[32];
-      coll += wemu::run_warp([&] { results[wemu::lane()] = bgxk::decode_page_warp(job, sm); });
+      bgxk::PageResult results[64];
+      coll += wemu::run_block(2, [&] { results[wemu::thread_id()] = bgxk::decode_page_cta(job, sm); });
       res = results[0];
-      for (int l = 1; l < 32; ++l)
+      for (int l = 1; l < 64; ++l)
         if (results[l].status != res.status || results[l].is_delta != res.is_delta) res.status |= 0x80000000u;
       if (!res.status && res.is_delta)
         coll += wemu::run_warp([&] { bgxk::delta_decode_warp(dst + e.out_off, e.out_off, e.out_size, planes_desc); });

@@ -30,62 +30,76 @@
 
 namespace wemu {
 
-enum Op : int { OP_NONE = 0, OP_SHFL, OP_SHFL_UP, OP_SHFL_DOWN, OP_SHFL_XOR, OP_BALLOT, OP_SYNC, OP_MATCH, OP_REDUCE };
+enum Op : int { OP_NONE = 0, OP_SHFL, OP_SHFL_UP, OP_SHFL_DOWN, OP_SHFL_XOR, OP_BALLOT, OP_SYNC, OP_MATCH, OP_REDUCE, OP_BLOCKSYNC };
 
-struct Warp {
-  ucontext_t sched;
-  ucontext_t ctx[32];
-  char* stack[32];
-  bool done[32];
-  int cur = 0;
-  // collective rendezvous
-  uint64_t slot[32];
-  uint32_t aux[32];
-  int op[32];
+constexpr int kMaxWarps = 4;
+
+struct Rendezvous {          // one per warp, plus one for the whole block (__syncthreads)
+  uint64_t slot[32 * kMaxWarps];
+  uint32_t aux[32 * kMaxWarps];
+  int op[32 * kMaxWarps];
   int arrived = 0;
   uint64_t gen = 0;
-  uint64_t result[2][32];
-  uint32_t result_aux[2][32];
+  uint64_t result[2][32 * kMaxWarps];
+  uint32_t result_aux[2][32 * kMaxWarps];
+};
+
+struct Block {
+  ucontext_t sched;
+  ucontext_t ctx[32 * kMaxWarps];
+  char* stack[32 * kMaxWarps];
+  bool done[32 * kMaxWarps];
+  int nthreads = 32;
+  int cur = 0;
+  Rendezvous warp[kMaxWarps];
+  Rendezvous block;
   uint64_t collectives = 0;
   std::function<void()> body;
 };
 
-inline Warp*& W() {
-  static thread_local Warp* w = nullptr;
-  return w;
+inline Block*& B() {
+  static thread_local Block* b = nullptr;
+  return b;
 }
-inline int lane() { return W()->cur; }
+inline int lane() { return B()->cur & 31; }
+inline int warp_id() { return B()->cur >> 5; }
+inline int thread_id() { return B()->cur; }
 
 inline void yield_to_sched() {
-  Warp* w = W();
-  swapcontext(&w->ctx[w->cur], &w->sched);
+  Block* b = B();
+  swapcontext(&b->ctx[b->cur], &b->sched);
 }
 
-// All 32 lanes contribute (v, aux); afterwards every lane can see everybody's contribution.
-inline void rendezvous(int op, uint64_t v, uint32_t aux, const uint64_t** vals, const uint32_t** auxs) {
-  Warp* w = W();
-  const int me = w->cur;
-  w->slot[me] = v;
-  w->aux[me] = aux;
-  w->op[me] = op;
-  const uint64_t mygen = w->gen;
-  if (++w->arrived == 32) {
-    for (int i = 0; i < 32; ++i) {
-      if (w->op[i] != op) {
-        fprintf(stderr, "warp_emul: lanes disagree on the collective (lane %d op %d vs lane %d op %d)\n", i, w->op[i], me, op);
+// All `count` participants contribute (v, aux); afterwards each can see everybody's contribution.
+// `me` is the participant index inside the rendezvous (lane for a warp, thread id for the block).
+inline void rendezvous(Rendezvous& r, int count, int me, int op, uint64_t v, uint32_t aux, const uint64_t** vals,
+                       const uint32_t** auxs) {
+  Block* b = B();
+  r.slot[me] = v;
+  r.aux[me] = aux;
+  r.op[me] = op;
+  const uint64_t mygen = r.gen;
+  if (++r.arrived == count) {
+    for (int i = 0; i < count; ++i) {
+      if (r.op[i] != op) {
+        fprintf(stderr, "warp_emul: participants disagree on the collective (%d: op %d vs %d: op %d)\n", i, r.op[i], me, op);
         abort();
       }
-      w->result[mygen & 1][i] = w->slot[i];
-      w->result_aux[mygen & 1][i] = w->aux[i];
+      r.result[mygen & 1][i] = r.slot[i];
+      r.result_aux[mygen & 1][i] = r.aux[i];
     }
-    w->arrived = 0;
-    w->collectives++;
-    w->gen++;
+    r.arrived = 0;
+    b->collectives++;
+    r.gen++;
   } else {
-    while (w->gen == mygen) yield_to_sched();
+    while (r.gen == mygen) yield_to_sched();
   }
-  *vals = w->result[mygen & 1];
-  *auxs = w->result_aux[mygen & 1];
+  *vals = r.result[mygen & 1];
+  *auxs = r.result_aux[mygen & 1];
+}
+inline void rendezvous(int op, uint64_t v, uint32_t aux, const uint64_t** vals, const uint32_t** auxs) {
+  Block* b = B();
+  rendezvous(b->warp[b->cur >> 5], 32, b->cur & 31, op, v, aux, vals, auxs);
 }
 
 inline void check_mask(unsigned mask) {
@@ -96,60 +110,64 @@ inline void check_mask(unsigned mask) {
 }
 
 inline void fiber_entry() {
-  Warp* w = W();
-  w->body();
-  w->done[w->cur] = true;
-  swapcontext(&w->ctx[w->cur], &w->sched);
+  Block* b = B();
+  b->body();
+  b->done[b->cur] = true;
+  swapcontext(&b->ctx[b->cur], &b->sched);
 }
 
-// Runs body() once per lane (32 fibers) to completion. Returns number of collectives executed.
-inline uint64_t run_warp(const std::function<void()>& body) {
-  Warp* w = new Warp();
-  Warp* saved = W();
-  W() = w;
-  w->body = body;
+// Runs body() once per thread of a block of `nwarps` warps to completion. Returns the number of collectives.
+inline uint64_t run_block(int nwarps, const std::function<void()>& body) {
+  Block* b = new Block();
+  Block* saved = B();
+  B() = b;
+  b->body = body;
+  b->nthreads = 32 * nwarps;
   const size_t kStack = 256 * 1024;
-  for (int i = 0; i < 32; ++i) {
-    w->stack[i] = (char*)malloc(kStack);
-    w->done[i] = false;
-    getcontext(&w->ctx[i]);
-    w->ctx[i].uc_stack.ss_sp = w->stack[i];
-    w->ctx[i].uc_stack.ss_size = kStack;
-    w->ctx[i].uc_link = &w->sched;
-    makecontext(&w->ctx[i], (void (*)())fiber_entry, 0);
+  for (int i = 0; i < b->nthreads; ++i) {
+    b->stack[i] = (char*)malloc(kStack);
+    b->done[i] = false;
+    getcontext(&b->ctx[i]);
+    b->ctx[i].uc_stack.ss_sp = b->stack[i];
+    b->ctx[i].uc_stack.ss_size = kStack;
+    b->ctx[i].uc_link = &b->sched;
+    makecontext(&b->ctx[i], (void (*)())fiber_entry, 0);
   }
-  int remaining = 32;
-  uint64_t last_gen = ~0ull;
+  int remaining = b->nthreads;
   int idle_sweeps = 0;
   while (remaining > 0) {
-    const uint64_t gen_before = w->gen;
-    int ran = 0;
-    for (int i = 0; i < 32; ++i) {
-      if (w->done[i]) continue;
-      w->cur = i;
-      swapcontext(&w->sched, &w->ctx[i]);
-      ++ran;
-      if (w->done[i]) --remaining;
+    const uint64_t before = b->collectives;
+    const int rem_before = remaining;
+    for (int i = 0; i < b->nthreads; ++i) {
+      if (b->done[i]) continue;
+      b->cur = i;
+      swapcontext(&b->sched, &b->ctx[i]);
+      if (b->done[i]) --remaining;
     }
-    if (w->gen == gen_before && remaining > 0) {
-      // nobody completed a collective in a full sweep: either some lanes exited while others wait,
-      // or lanes are parked at different collectives -> deadlock in real hardware terms.
+    if (b->collectives == before && remaining == rem_before && remaining > 0) {
+      // nobody completed a collective or finished in a full sweep: threads are parked at collectives
+      // that can never complete -> deadlock in real hardware terms.
       if (++idle_sweeps > 2) {
-        fprintf(stderr, "warp_emul: deadlock (%d lanes alive, %d arrived at a collective)\n", remaining, w->arrived);
+        fprintf(stderr, "warp_emul: deadlock (%d threads alive; block barrier has %d arrivals", remaining, b->block.arrived);
+        for (int w = 0; w < b->nthreads / 32; ++w) {
+          int alive = 0;
+          for (int t = 0; t < 32; ++t) alive += !b->done[w * 32 + t];
+          fprintf(stderr, "; warp %d: %d alive, %d at a warp collective (op %d)", w, alive, b->warp[w].arrived, b->warp[w].op[0]);
+        }
+        fprintf(stderr, ")\n");
         abort();
       }
     } else {
       idle_sweeps = 0;
     }
-    (void)last_gen;
-    (void)ran;
   }
-  const uint64_t n = w->collectives;
-  for (int i = 0; i < 32; ++i) free(w->stack[i]);
-  delete w;
-  W() = saved;
+  const uint64_t n = b->collectives;
+  for (int i = 0; i < b->nthreads; ++i) free(b->stack[i]);
+  delete b;
+  B() = saved;
   return n;
 }
+inline uint64_t run_warp(const std::function<void()>& body) { return run_block(1, body); }
 
 }  // namespace wemu
 
@@ -223,6 +241,12 @@ inline void __syncwarp(unsigned mask = 0xffffffffu) {
   const uint64_t* vals;
   const uint32_t* auxs;
   wemu::rendezvous(wemu::OP_SYNC, 0, 0, &vals, &auxs);
+}
+inline void __syncthreads() {
+  const uint64_t* vals;
+  const uint32_t* auxs;
+  wemu::Block* b = wemu::B();
+  wemu::rendezvous(b->block, b->nthreads, b->cur, wemu::OP_BLOCKSYNC, 0, 0, &vals, &auxs);
 }
 inline unsigned __match_any_sync(unsigned mask, unsigned v) {
   wemu::check_mask(mask);
