@@ -434,6 +434,29 @@ BGX_DEV uint32_t load_table(WarpSmem* sm, BitRd& rd, const PageIn& in, uint32_t 
   return 0;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Explicit shared-state-space accesses for the hot assembly loops. A `saddr_t` is a 32-bit
+// shared-window address on the device (so the loops issue plain `LDS/STS [R+imm]` instead of
+// re-deriving the generic address of the arena for every access) and a host pointer in the emulator.
+#ifdef BGX_EMULATED
+typedef uintptr_t saddr_t;
+BGX_DEV saddr_t saddr(const void* p) { return reinterpret_cast<uintptr_t>(p); }
+BGX_DEV uint32_t lds_u8(saddr_t a) { return *reinterpret_cast<const uint8_t*>(a); }
+BGX_DEV void sts_u8(saddr_t a, uint32_t v) { *reinterpret_cast<uint8_t*>(a) = (uint8_t)v; }
+BGX_DEV uint32_t lds_u32(saddr_t a) { return *reinterpret_cast<const uint32_t*>(a); }
+BGX_DEV uint2 lds_u32x2(saddr_t a) { return *reinterpret_cast<const uint2*>(a); }
+BGX_DEV uint32_t ldg_u8(const uint8_t* p) { return *p; }
+#else
+typedef uint32_t saddr_t;
+BGX_DEV saddr_t saddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+BGX_DEV uint32_t lds_u8(saddr_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+BGX_DEV void sts_u8(saddr_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+BGX_DEV uint32_t lds_u32(saddr_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+BGX_DEV uint2 lds_u32x2(saddr_t a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
+BGX_DEV uint32_t ldg_u8(const uint8_t* p) { uint32_t v; asm volatile("ld.global.u8 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
+#endif
+
 // ---------------------------------------------------------------------------------------------
 struct PageJob {
   const uint8_t* in;        // compressed page (4-byte aligned)
@@ -646,9 +669,63 @@ BGX_DEV_NOINLINE PageResult decode_page_cta(const PageJob& job, WarpSmem* sm) {
           br_skip(r, in, len);
           rd = r;   // the sentinel's code bits are consumed; its lane then continues with literals
         }
+        // ---- distance ring, resolved by relaxation (PageDecoder.cpp:345-404)
+        {
+          const bool has_copy = cpy != 0;
+          const uint32_t dcode = (dx >> 31) ? (dx & 0xffu) : 16u;   // 16 = explicit distance
+          uint32_t dist = (dx >> 31) ? 0u : dx;
+          const uint32_t push = __ballot_sync(kFull, has_copy && dcode != 0);   // commands that enter the ring
+          const uint32_t below = push & lt_mask;
+          bool unresolved = has_copy && dcode < 16u;
+          uint32_t slot = 0;       // which ring slot (0..3) the short code refers to, and the offset applied to it
+          int32_t delta = 0;
+          if (unresolved) {
+            if (dcode < 4u) slot = dcode;
+            else {
+              const uint32_t c = dcode - 4u;              // 0..11
+              slot = c >= 6u ? 1u : 0u;
+              const uint32_t k = c >= 6u ? c - 6u : c;    // 0..5 => -1 +1 -2 +2 -3 +3
+              delta = (int32_t)(k >> 1) + 1;
+              if (!(k & 1u)) delta = -delta;
+            }
+          }
+          // source: the slot-th most recent pusher below me, else the carried ring
+          uint32_t b = below;
+          for (uint32_t k = 0; k < slot && b; ++k) b &= ~(1u << (31 - __clz((int)b)));
+          const uint32_t npush_below = __popc(below);
+          const bool from_carry = slot >= npush_below;
+          const uint32_t src_lane = from_carry ? 0u : (uint32_t)(31 - __clz((int)b));
+          const uint32_t cslot = slot - (from_carry ? npush_below : 0u);
+          const uint32_t carry_val = cslot == 0 ? r0 : cslot == 1 ? r1 : cslot == 2 ? r2 : r3;
+          uint32_t resolved = __ballot_sync(kFull, !unresolved);
+          while (resolved != kFull) {
+            BGX_STAT(emu_stats().ring_iters++);
+            const uint32_t v = __shfl_sync(kFull, dist, src_lane);
+            const bool ready = unresolved && (from_carry || ((resolved >> src_lane) & 1u));
+            if (ready) {
+              dist = (uint32_t)((int32_t)(from_carry ? carry_val : v) + delta);
+              unresolved = false;
+            }
+            resolved = __ballot_sync(kFull, !unresolved);
+          }
+          if (push) {   // new carried ring = four most recent pushers of this round, then the old ring
+            uint32_t pb = push;
+            uint32_t nr[4];
+            uint32_t old_idx = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint32_t hb = pb ? (uint32_t)(31 - __clz((int)pb)) : 0u;
+              const uint32_t v = __shfl_sync(kFull, dist, hb);
+              if (pb) { nr[k] = v; pb &= ~(1u << hb); }
+              else { nr[k] = old_idx == 0 ? r0 : old_idx == 1 ? r1 : old_idx == 2 ? r2 : r3; ++old_idx; }
+            }
+            r0 = nr[0]; r1 = nr[1]; r2 = nr[2]; r3 = nr[3];
+          }
+          dx = dist;
+        }
         rb->ins[lane] = ins;
         rb->cpy[lane] = cpy;
-        rb->dx[lane] = dx;
+        rb->dx[lane] = dx;            // final distance
         // ---- literals of this round (PageDecoder.cpp:196-206)
         const uint32_t round_ins = __reduce_add_sync(kFull, ins);
         const uint32_t round_out = round_ins + __reduce_add_sync(kFull, cpy);
@@ -754,8 +831,7 @@ BGX_DEV_NOINLINE PageResult decode_page_cta(const PageJob& job, WarpSmem* sm) {
         const uint32_t rflags = ctl->rflags[C & 1u];
         const uint32_t ins = rb->ins[lane], cpy = rb->cpy[lane], dx = rb->dx[lane];
         const bool has_copy = cpy != 0;
-        const uint32_t dcode = (dx >> 31) ? (dx & 0xffu) : 16u;   // 16 = explicit distance
-        uint32_t dist = (dx >> 31) ? 0u : dx;
+        const uint32_t dist = dx;            // resolved by the producer
         uint32_t err = 0;
         // ---- positions
         const uint32_t tot = ins + cpy;
@@ -768,63 +844,14 @@ BGX_DEV_NOINLINE PageResult decode_page_cta(const PageJob& job, WarpSmem* sm) {
         const uint32_t o_cpy = o_ins + ins;                 // where its copy goes
         if (round_out > out_size - pos) err = kPageErrOverrun;
         const uint32_t round_end = pos + round_out;
-        // ---- distance ring, resolved by relaxation (PageDecoder.cpp:345-404)
         {
-          const uint32_t push = __ballot_sync(kFull, has_copy && dcode != 0);   // commands that enter the ring
-          const uint32_t below = push & lt_mask;
-          bool unresolved = has_copy && dcode < 16u;
-          uint32_t slot = 0;       // which ring slot (0..3) the short code refers to, and the offset applied to it
-          int32_t delta = 0;
-          if (unresolved) {
-            if (dcode < 4u) slot = dcode;
-            else {
-              const uint32_t c = dcode - 4u;              // 0..11
-              slot = c >= 6u ? 1u : 0u;
-              const uint32_t k = c >= 6u ? c - 6u : c;    // 0..5 => -1 +1 -2 +2 -3 +3
-              delta = (int32_t)(k >> 1) + 1;
-              if (!(k & 1u)) delta = -delta;
-            }
-          }
-          // source: the slot-th most recent pusher below me, else the carried ring
-          uint32_t b = below;
-          for (uint32_t k = 0; k < slot && b; ++k) b &= ~(1u << (31 - __clz((int)b)));
-          const uint32_t npush_below = __popc(below);
-          const bool from_carry = slot >= npush_below;
-          const uint32_t src_lane = from_carry ? 0u : (uint32_t)(31 - __clz((int)b));
-          const uint32_t cslot = slot - (from_carry ? npush_below : 0u);
-          const uint32_t carry_val = cslot == 0 ? r0 : cslot == 1 ? r1 : cslot == 2 ? r2 : r3;
-          uint32_t resolved = __ballot_sync(kFull, !unresolved);
-          while (resolved != kFull) {
-            BGX_STAT(emu_stats().ring_iters++);
-            const uint32_t v = __shfl_sync(kFull, dist, src_lane);
-            const bool ready = unresolved && (from_carry || ((resolved >> src_lane) & 1u));
-            if (ready) {
-              dist = (uint32_t)((int32_t)(from_carry ? carry_val : v) + delta);
-              unresolved = false;
-            }
-            resolved = __ballot_sync(kFull, !unresolved);
-          }
-          if (push) {   // new carried ring = four most recent pushers of this round, then the old ring
-            uint32_t pb = push;
-            uint32_t nr[4];
-            uint32_t old_idx = 0;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint32_t hb = pb ? (uint32_t)(31 - __clz((int)pb)) : 0u;
-              const uint32_t v = __shfl_sync(kFull, dist, hb);
-              if (pb) { nr[k] = v; pb &= ~(1u << hb); }
-              else { nr[k] = old_idx == 0 ? r0 : old_idx == 1 ? r1 : old_idx == 2 ? r2 : r3; ++old_idx; }
-            }
-            r0 = nr[0]; r1 = nr[1]; r2 = nr[2]; r3 = nr[3];
-          }
           const uint32_t baddist = __ballot_sync(kFull, has_copy && (dist == 0 || dist > o_cpy));
           if (baddist && !err) err = kPageErrDistance;
         }
         if (err) {
           if (lane == 0) ctl->err = err;
         } else if (rflags & 2u) {
-          // ---- slow round: hand the resolved distances and a fully flushed page over to the producer
-          rb->dx[lane] = dist;
+          // ---- slow round: hand a fully flushed page over to the producer
           flush_bytes(sm, out, flushed, pos, lane);
           flushed = pos;
           await_slow = true;
@@ -847,20 +874,24 @@ BGX_DEV_NOINLINE PageResult decode_page_cta(const PageJob& job, WarpSmem* sm) {
           //      Commands with literals are compacted into tab[]; a per-chunk bit mask of their first
           //      literal index turns "which command owns literal t" into one popc.
           uint32_t* tab = sm->scratch;                       // [32] (o_ins - first literal index)
-          uint4* tab2 = reinterpret_cast<uint4*>(sm->scratch + 32);   // [32] (dst - first flat index, distance, dst start)
+          const saddr_t ring_a = saddr(sm->ring), litq_a = saddr(sm->litq), tab_a = saddr(sm->scratch);
           {
             const uint32_t has = __ballot_sync(kFull, ins != 0);
             if (ins) tab[__popc(has & lt_mask)] = o_ins - lq;
             __syncwarp();
+            const uint32_t icidx = lq >> 5;
+            const uint32_t icbit = ins ? (1u << (lq & 31u)) : 0u;
+            const uint32_t ilast = __popc(has) - 1u;
             uint32_t before = 0;
-            for (uint32_t c0 = 0; c0 < round_ins; c0 += 32) {
-              const uint32_t M = __reduce_or_sync(kFull, (ins && lq - c0 < 32u) ? (1u << (lq - c0)) : 0u);
+            for (uint32_t c = 0, c0 = 0; c0 < round_ins; ++c, c0 += 32) {
+              const uint32_t M = __reduce_or_sync(kFull, icidx == c ? icbit : 0u);
               const uint32_t t = c0 + lane;
-              if (t < round_ins) {
-                const uint32_t ord = before + __popc(M & le_mask) - 1u;
-                sm->ring[(tab[ord] + t) & (kRing - 1)] = sm->litq[(lit_head + t) & (kLitQ - 1)];
-              }
+              uint32_t ord = before + __popc(M & le_mask) - 1u;
               before += __popc(M);
+              ord = ord < ilast ? ord : ilast;
+              const uint32_t base = lds_u32(tab_a + 4u * ord);
+              const uint32_t v = lds_u8(litq_a + ((lit_head + t) & (kLitQ - 1)));
+              if (t < round_ins) sts_u8(ring_a + ((base + t) & (kRing - 1)), v);
             }
           }
           __syncwarp();
@@ -873,43 +904,52 @@ BGX_DEV_NOINLINE PageResult decode_page_cta(const PageJob& job, WarpSmem* sm) {
           if (pending) {
             const int first = __ffs((int)pending) - 1;
             const uint32_t hwm = __shfl_sync(kFull, o_cpy, first);           // everything below is final
-            const bool ready1 = cpy != 0 && ((int)lane == first || src_hi <= hwm);
+            const bool ready1 = cpy != 0 && dist >= cpy && ((int)lane == first || src_hi <= hwm);
             const uint32_t len1 = ready1 ? cpy : 0u;
             const uint32_t E1 = warp_incl_scan(len1, lane);
             const uint32_t T1 = __shfl_sync(kFull, E1, 31);
             const uint32_t S1 = E1 - len1;
             const uint32_t m1 = __ballot_sync(kFull, ready1);
-            if (ready1) tab2[__popc(m1 & lt_mask)] = make_uint4(o_cpy - S1, dist, o_cpy, 0u);
+            uint2* tab2 = reinterpret_cast<uint2*>(sm->scratch + 32);        // [32] (dst - first flat index, distance)
+            if (ready1) tab2[__popc(m1 & lt_mask)] = make_uint2(o_cpy - S1, dist);
             __syncwarp();
+            const uint32_t cidx = S1 >> 5;
+            const uint32_t cbit = ready1 ? (1u << (S1 & 31u)) : 0u;
+            const uint32_t last = __popc(m1) - 1u;
             uint32_t before = 0;
-            for (uint32_t c0 = 0; c0 < T1; c0 += 128) {      // four 32-byte chunks per trip: all loads go out before the stores
+            const saddr_t tab2_a = tab_a + 128u;
+            for (uint32_t c = 0, c0 = 0; c0 < T1; c += 4, c0 += 128) {       // four 32-byte chunks per trip: loads before stores
+              uint32_t M[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) M[u] = __reduce_or_sync(kFull, cidx == c + u ? cbit : 0u);
               uint32_t d[4];
-              uint8_t v[4];
+              uint32_t v[4];
 #pragma unroll
               for (int u = 0; u < 4; ++u) {
-                const uint32_t cu = c0 + 32u * u;
-                const uint32_t M = __reduce_or_sync(kFull, (ready1 && S1 - cu < 32u) ? (1u << (S1 - cu)) : 0u);
-                const uint32_t t = cu + lane;
-                d[u] = 0xffffffffu;
+                const uint32_t t = c0 + 32u * u + lane;
+                uint32_t ord = before + __popc(M[u] & le_mask) - 1u;
+                before += __popc(M[u]);
+                ord = ord < last ? ord : last;                               // lanes past the end read a valid entry
+                const uint2 q = lds_u32x2(tab2_a + 8u * ord);
+                d[u] = q.x + t;
+                const uint32_t sp = d[u] - q.y;
+                const bool ok = t < T1;
+                const bool near = (int32_t)sp >= ring_lo;
                 v[u] = 0;
-                if (t < T1) {
-                  const uint4 q = tab2[before + __popc(M & le_mask) - 1u];
-                  d[u] = q.x + t;
-                  uint32_t j = d[u] - q.z;            // byte index inside the copy
-                  if (j >= q.y) j %= q.y;             // overlapping copy: pattern of `dist` bytes repeats (PageDecoder.cpp:222-232)
-                  v[u] = out_byte(sm, out, ring_lo, q.z - q.y + j);
-                }
-                before += __popc(M);
+                if (ok && near) v[u] = lds_u8(ring_a + (sp & (kRing - 1)));
+                if (ok && !near) v[u] = ldg_u8(out + sp);
+                if (!ok) d[u] = 0xffffffffu;
               }
 #pragma unroll
               for (int u = 0; u < 4; ++u)
-                if (d[u] != 0xffffffffu) sm->ring[d[u] & (kRing - 1)] = v[u];
+                if (d[u] != 0xffffffffu) sts_u8(ring_a + (d[u] & (kRing - 1)), v[u]);
             }
             __syncwarp();
             pending &= ~m1;
           }
-          //      Remaining copies (dependent on this round's copies): in wavefronts, one lane per
-          //      command, byte-serial (exact overlap semantics); long ones by the whole warp.
+          //      Remaining copies (dependent on this round's copies, or overlapping themselves): in
+          //      wavefronts, one lane per command, byte-serial (exact overlap semantics). Their sources
+          //      lie inside this round or just before it, i.e. always in the ring.
           while (pending) {
             const int first = __ffs((int)pending) - 1;
             const uint32_t hwm = __shfl_sync(kFull, o_cpy, first);
@@ -922,8 +962,17 @@ BGX_DEV_NOINLINE PageResult decode_page_cta(const PageJob& job, WarpSmem* sm) {
             }
 #endif
             if (ready && cpy < kCoopLen) {
-              for (uint32_t j = 0; j < cpy; ++j)
-                sm->ring[(o_cpy + j) & (kRing - 1)] = out_byte(sm, out, ring_lo, src_lo + j);
+              if ((int32_t)src_lo >= ring_lo) {
+                uint32_t sa = src_lo & (kRing - 1), da = o_cpy & (kRing - 1);
+#pragma unroll 1
+                for (uint32_t j = 0; j < cpy; ++j) {
+                  sts_u8(ring_a + da, lds_u8(ring_a + sa));
+                  sa = (sa + 1) & (kRing - 1);
+                  da = (da + 1) & (kRing - 1);
+                }
+              } else {
+                for (uint32_t j = 0; j < cpy; ++j) sm->ring[(o_cpy + j) & (kRing - 1)] = out_byte(sm, out, ring_lo, src_lo + j);
+              }
             }
             const uint32_t ready_mask = __ballot_sync(kFull, ready);
             uint32_t bigc = __ballot_sync(kFull, ready && cpy >= kCoopLen);
