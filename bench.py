@@ -128,6 +128,22 @@ def make_workload(kind: str, total_bytes: int, seed0: int, sdk, threads: int = 0
             if i == 0:
                 verify = (0, d)
         return streams, usizes, verify, {"unique_streams": n_streams, "replicas": 1}
+    if kind == "texture":
+        # BASELINE configs[2]: block-compressed textures with pre-conditioning (the reference has BC1..BC5, no BC7):
+        # 1024x1024-block BC3 (16 MiB each), swizzle + delta, one mip
+        from brotli_g_sdk_b200.encoder import DataconditionParams
+        tex_bytes = 1024 * 1024 * 16
+        n_tex = max(1, total_bytes // tex_bytes)
+        unique = min(n_tex, 4)
+        p = DataconditionParams(precondition=True, swizzle=True, delta_encode=True, format=3, width_blocks=1024, height_blocks=1024)
+        for i in range(unique):
+            d = datagen.bc_texture(1024, 1024, 3, seed=seed0 + i)
+            streams.append(sdk.Encode(d, page_size=PAGE, dcParams=p, num_threads=threads))
+            usizes.append(len(d))
+            if i == 0:
+                verify = (0, d)
+        reps = (n_tex + unique - 1) // unique
+        return (streams * reps)[:n_tex], (usizes * reps)[:n_tex], verify, {"unique_streams": unique, "replicas": reps}
     # compressible payloads: encode a bounded number of unique streams, replicate them to the requested size
     gen = {"mixed": datagen.mixed, "text": datagen.text_like, "binary": datagen.structured_binary, "lowent": datagen.low_entropy}[kind]
     unique = min(n_streams, 4)
@@ -231,7 +247,8 @@ def run_reference_arm(args):
 def workload_config(args, rep):
     names = {"random": "configs[1]: 4 GiB random-byte buffer, page_size=65536 (64 streams x 64 MiB, all pages raw)",
              "mixed": "configs[3]-like: mixed-entropy (text+binary+random) 64 MiB streams, page_size=65536",
-             "text": "text-like 64 MiB streams, page_size=65536"}
+             "text": "text-like 64 MiB streams, page_size=65536",
+             "texture": "configs[2]: BC3 textures 1024x1024 blocks (16 MiB), pre-conditioned (swizzle + delta), page_size=65536"}
     return {"workload": names.get(args.workload, args.workload), "bytes_per_gpu": args.size_gib << 30, "page_size": PAGE,
             "streams_per_gpu": max(1, (args.size_gib << 30) // STREAM_BYTES), "stream_bytes": STREAM_BYTES, **rep,
             "l2_policy": "inputs+outputs per step (>= 2x payload) are far larger than the 126 MB L2; no flush needed",
@@ -405,7 +422,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="random", choices=["random", "mixed", "text", "binary", "lowent"])
+    ap.add_argument("--workload", default="random", choices=["random", "mixed", "text", "binary", "lowent", "texture"])
     ap.add_argument("--size-gib", type=int, default=4)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

@@ -486,12 +486,23 @@ BGX_DEV void flush_bytes(const WarpSmem* sm, uint8_t* out, uint32_t from, uint32
 // page-global literal indices tail + j*32 + lane.
 BGX_DEV void decode_literals(WarpSmem* sm, BitRd& rd, const PageIn& in, uint32_t tail, uint32_t cnt, uint32_t lane) {
   uint32_t q = (tail + lane) & (kLitQ - 1);
-  for (uint32_t j = 0; j < cnt; ++j) {
+  uint32_t j = 0;
+  // two literals per 32-bit peek (2 x 15 bits at most): one window refill check per pair
+  for (; j + 2 <= cnt; j += 2) {
+    const uint32_t pk = br_peek(rd);
+    uint32_t len1, len2;
+    const uint32_t s1 = huff_decode<kLitLutBits>(sm->lut_lit, sm->aux[2], sm->sorted_lit, bgx::kNumLitSymbols, pk, len1);
+    const uint32_t s2 = huff_decode<kLitLutBits>(sm->lut_lit, sm->aux[2], sm->sorted_lit, bgx::kNumLitSymbols, pk >> len1, len2);
+    sm->litq[q] = (uint8_t)s1;
+    sm->litq[(q + 32) & (kLitQ - 1)] = (uint8_t)s2;
+    q = (q + 64) & (kLitQ - 1);
+    br_skip(rd, in, len1 + len2);
+  }
+  if (j < cnt) {
     uint32_t len;
     const uint32_t sym = huff_decode<kLitLutBits>(sm->lut_lit, sm->aux[2], sm->sorted_lit, bgx::kNumLitSymbols,
                                                   br_peek(rd), len);
     sm->litq[q] = (uint8_t)sym;
-    q = (q + 32) & (kLitQ - 1);
     br_skip(rd, in, len);
   }
 }
@@ -675,6 +686,8 @@ BGX_DEV_NOINLINE PageResult decode_page_cta(const PageJob& job, WarpSmem* sm) {
           const uint32_t dcode = (dx >> 31) ? (dx & 0xffu) : 16u;   // 16 = explicit distance
           uint32_t dist = (dx >> 31) ? 0u : dx;
           const uint32_t push = __ballot_sync(kFull, has_copy && dcode != 0);   // commands that enter the ring
+          const uint32_t any_short = __ballot_sync(kFull, has_copy && dcode < 16u);
+          if (any_short) {
           const uint32_t below = push & lt_mask;
           bool unresolved = has_copy && dcode < 16u;
           uint32_t slot = 0;       // which ring slot (0..3) the short code refers to, and the offset applied to it
@@ -707,6 +720,7 @@ BGX_DEV_NOINLINE PageResult decode_page_cta(const PageJob& job, WarpSmem* sm) {
               unresolved = false;
             }
             resolved = __ballot_sync(kFull, !unresolved);
+          }
           }
           if (push) {   // new carried ring = four most recent pushers of this round, then the old ring
             uint32_t pb = push;
