@@ -28,6 +28,8 @@
 #pragma once
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "bgx_format.h"
 
 #ifndef BGX_EMULATED
@@ -78,7 +80,9 @@ struct HuffAux {
 struct RoundBuf {            // one round of <= 32 commands, producer -> consumer
   uint32_t ins[32];
   uint32_t cpy[32];          // 0 = no copy (insert-only command or no command)
-  uint32_t dx[32];           // explicit distance, or 0x80000000 | short code 0..15 (to be resolved by the consumer)
+  uint32_t dx[32];           // resolved match distance
+  uint32_t itot[32];         // inclusive prefix sum of ins + cpy: this command's output ends at round start + itot
+  uint32_t iins[32];         // inclusive prefix sum of ins: its literals end at literal index iins of the round
 };
 struct PageCtl {             // hand-over state of the two warps of a page (read after, written before a barrier)
   uint32_t produced, consumed;   // rounds published by the producer / retired by the consumer
@@ -737,12 +741,16 @@ BGX_DEV_NOINLINE PageResult decode_page_cta(const PageJob& job, WarpSmem* sm) {
           }
           dx = dist;
         }
+        // ---- positions: one 64-bit warp scan gives every command its output and literal offsets
+        const uint64_t incl_both = warp_incl_scan64(((uint64_t)(ins + cpy) << 32) | ins, lane);
         rb->ins[lane] = ins;
         rb->cpy[lane] = cpy;
         rb->dx[lane] = dx;            // final distance
+        rb->itot[lane] = (uint32_t)(incl_both >> 32);
+        rb->iins[lane] = (uint32_t)incl_both;
         // ---- literals of this round (PageDecoder.cpp:196-206)
-        const uint32_t round_ins = __reduce_add_sync(kFull, ins);
-        const uint32_t round_out = round_ins + __reduce_add_sync(kFull, cpy);
+        const uint32_t round_ins = __shfl_sync(kFull, (uint32_t)incl_both, 31);
+        const uint32_t round_out = __shfl_sync(kFull, (uint32_t)(incl_both >> 32), 31);
         const uint32_t avail = lit_tail - lit_head_p;     // decoded ahead of need in earlier rounds (< 32)
         const uint32_t need = round_ins > avail ? round_ins - avail : 0u;
         const uint32_t mult = n ? (n == 32u ? (need + 31u) >> 5 : (need + n - 1u) / n) : 0u;
@@ -849,11 +857,10 @@ BGX_DEV_NOINLINE PageResult decode_page_cta(const PageJob& job, WarpSmem* sm) {
         uint32_t err = 0;
         // ---- positions
         const uint32_t tot = ins + cpy;
-        const uint64_t incl_both = warp_incl_scan64(((uint64_t)tot << 32) | ins, lane);
-        const uint32_t incl_tot = (uint32_t)(incl_both >> 32);
-        const uint32_t incl_ins = (uint32_t)incl_both;
-        const uint32_t round_out = __shfl_sync(kFull, incl_tot, 31);
-        const uint32_t round_ins = __shfl_sync(kFull, incl_ins, 31);
+        const uint32_t incl_tot = rb->itot[lane];
+        const uint32_t incl_ins = rb->iins[lane];
+        const uint32_t round_out = rb->itot[31];
+        const uint32_t round_ins = rb->iins[31];
         const uint32_t o_ins = pos + incl_tot - tot;        // where this command's literals go
         const uint32_t o_cpy = o_ins + ins;                 // where its copy goes
         if (round_out > out_size - pos) err = kPageErrOverrun;
@@ -912,8 +919,7 @@ BGX_DEV_NOINLINE PageResult decode_page_cta(const PageJob& job, WarpSmem* sm) {
           // ---- copies. Wavefront 1 (flattened, like the inserts): every copy whose source already is
           //      final, i.e. lies below the destination of the first pending copy. Sources may be in
           //      the ring or (far matches) in L1/L2.
-          const uint32_t src_lo = o_cpy - dist;                              // first source byte
-          const uint32_t src_hi = src_lo + (cpy < dist ? cpy : dist);        // one past the last distinct source byte
+          const uint32_t src_hi = o_cpy - dist + (cpy < dist ? cpy : dist);  // one past the last distinct source byte
           uint32_t pending = __ballot_sync(kFull, cpy != 0);
           if (pending) {
             const int first = __ffs((int)pending) - 1;
@@ -932,14 +938,16 @@ BGX_DEV_NOINLINE PageResult decode_page_cta(const PageJob& job, WarpSmem* sm) {
             const uint32_t last = __popc(m1) - 1u;
             uint32_t before = 0;
             const saddr_t tab2_a = tab_a + 128u;
-            for (uint32_t c = 0, c0 = 0; c0 < T1; c += 4, c0 += 128) {       // four 32-byte chunks per trip: loads before stores
-              uint32_t M[4];
+            // NU 32-byte chunks per trip; all loads of a trip are issued before its stores
+            auto trip = [&](auto nu_tag, uint32_t c, uint32_t c0) {
+              constexpr int NU = decltype(nu_tag)::value;
+              uint32_t M[NU];
 #pragma unroll
-              for (int u = 0; u < 4; ++u) M[u] = __reduce_or_sync(kFull, cidx == c + u ? cbit : 0u);
-              uint32_t d[4];
-              uint32_t v[4];
+              for (int u = 0; u < NU; ++u) M[u] = __reduce_or_sync(kFull, cidx == c + u ? cbit : 0u);
+              uint32_t d[NU];
+              uint32_t v[NU];
 #pragma unroll
-              for (int u = 0; u < 4; ++u) {
+              for (int u = 0; u < NU; ++u) {
                 const uint32_t t = c0 + 32u * u + lane;
                 uint32_t ord = before + __popc(M[u] & le_mask) - 1u;
                 before += __popc(M[u]);
@@ -955,57 +963,36 @@ BGX_DEV_NOINLINE PageResult decode_page_cta(const PageJob& job, WarpSmem* sm) {
                 if (!ok) d[u] = 0xffffffffu;
               }
 #pragma unroll
-              for (int u = 0; u < 4; ++u)
+              for (int u = 0; u < NU; ++u)
                 if (d[u] != 0xffffffffu) sts_u8(ring_a + (d[u] & (kRing - 1)), v[u]);
+            };
+            uint32_t c = 0, c0 = 0;
+            for (; c0 + 64u < T1; c += 4, c0 += 128) trip(std::integral_constant<int, 4>{}, c, c0);
+            if (c0 < T1) {
+              if (T1 - c0 > 32u) trip(std::integral_constant<int, 2>{}, c, c0);
+              else trip(std::integral_constant<int, 1>{}, c, c0);
             }
             __syncwarp();
             pending &= ~m1;
           }
-          //      Remaining copies (dependent on this round's copies, or overlapping themselves): in
-          //      wavefronts, one lane per command, byte-serial (exact overlap semantics). Their sources
-          //      lie inside this round or just before it, i.e. always in the ring.
+          //      Remaining copies (dependent on this round's copies, or overlapping themselves): in command
+          //      order, each by the whole warp (lane j moves byte j; almost always a single step). In-order
+          //      execution satisfies every dependency; an overlapping copy (dist < len) repeats its
+          //      `dist`-byte pattern exactly as the byte-serial reference loop does (PageDecoder.cpp:222-232).
           while (pending) {
-            const int first = __ffs((int)pending) - 1;
-            const uint32_t hwm = __shfl_sync(kFull, o_cpy, first);
-            const bool ready = ((pending >> lane) & 1u) && ((int)lane == first || src_hi <= hwm);
-#ifdef BGX_STATS
-            {
-              const uint32_t mc = __reduce_max_sync(kFull, (ready && cpy < kCoopLen) ? cpy : 0u);
-              const uint32_t nc = __popc(__ballot_sync(kFull, ready && cpy >= kCoopLen));
-              BGX_STAT(emu_stats().wavefronts++; emu_stats().sum_max_cpy += mc; emu_stats().coop_copies += nc);
+            const int k = __ffs((int)pending) - 1;
+            pending &= pending - 1;
+            const uint32_t n_k = __shfl_sync(kFull, cpy, k);
+            const uint32_t o_k = __shfl_sync(kFull, o_cpy, k);
+            const uint32_t d_k = __shfl_sync(kFull, dist, k);
+            BGX_STAT(emu_stats().wavefronts++; emu_stats().sum_max_cpy += n_k);
+            for (uint32_t j = lane; j < n_k; j += 32) {
+              const uint32_t m = j < d_k ? j : j % d_k;
+              const uint32_t sp = o_k - d_k + m;
+              const uint32_t v = ((int32_t)sp >= ring_lo) ? lds_u8(ring_a + (sp & (kRing - 1))) : ldg_u8(out + sp);
+              sts_u8(ring_a + ((o_k + j) & (kRing - 1)), v);
             }
-#endif
-            if (ready && cpy < kCoopLen) {
-              if ((int32_t)src_lo >= ring_lo) {
-                uint32_t sa = src_lo & (kRing - 1), da = o_cpy & (kRing - 1);
-#pragma unroll 1
-                for (uint32_t j = 0; j < cpy; ++j) {
-                  sts_u8(ring_a + da, lds_u8(ring_a + sa));
-                  sa = (sa + 1) & (kRing - 1);
-                  da = (da + 1) & (kRing - 1);
-                }
-              } else {
-                for (uint32_t j = 0; j < cpy; ++j) sm->ring[(o_cpy + j) & (kRing - 1)] = out_byte(sm, out, ring_lo, src_lo + j);
-              }
-            }
-            const uint32_t ready_mask = __ballot_sync(kFull, ready);
-            uint32_t bigc = __ballot_sync(kFull, ready && cpy >= kCoopLen);
             __syncwarp();
-            while (bigc) {
-              const int k = __ffs((int)bigc) - 1;
-              bigc &= bigc - 1;
-              const uint32_t n_k = __shfl_sync(kFull, cpy, k);
-              const uint32_t o_k = __shfl_sync(kFull, o_cpy, k);
-              const uint32_t d_k = __shfl_sync(kFull, dist, k);
-              const uint32_t s_k = o_k - d_k;
-              // byte j of the copy = pattern byte (j mod dist) of the dist bytes preceding the destination
-              for (uint32_t j = lane; j < n_k; j += 32) {
-                const uint32_t m = j < d_k ? j : j % d_k;
-                sm->ring[(o_k + j) & (kRing - 1)] = out_byte(sm, out, ring_lo, s_k + m);
-              }
-              __syncwarp();
-            }
-            pending &= ~ready_mask;
           }
           pos = round_end;
           lit_head += round_ins;
