@@ -56,7 +56,7 @@ constexpr unsigned kFull = 0xffffffffu;
 constexpr int kCmdLutBits = 9;
 constexpr int kLitLutBits = 10;
 constexpr int kDistLutBits = 9;
-constexpr uint32_t kLitQ = 1024;      // literal ring bytes (power of two): two rounds' literals (producer runs one ahead)
+constexpr uint32_t kLitQ = 512;       // literal ring bytes (power of two): two rounds' literals (producer runs one ahead)
 constexpr uint32_t kRing = 2048;      // output ring bytes (power of two, >= kFlushChunk + kRoundMax)
 constexpr uint32_t kRoundMax = 1024;  // largest round (bytes produced) the ring path accepts
 constexpr uint32_t kFlushChunk = 512; // 32 lanes x 16 B
@@ -78,11 +78,11 @@ struct HuffAux {
 };
 
 struct RoundBuf {            // one round of <= 32 commands, producer -> consumer
-  uint32_t ins[32];
-  uint32_t cpy[32];          // 0 = no copy (insert-only command or no command)
   uint32_t dx[32];           // resolved match distance
-  uint32_t itot[32];         // inclusive prefix sum of ins + cpy: this command's output ends at round start + itot
-  uint32_t iins[32];         // inclusive prefix sum of ins: its literals end at literal index iins of the round
+  uint16_t ins[32];          // 16-bit fields: only rounds of <= kRoundMax bytes are handed over through them
+  uint16_t cpy[32];          // (0 = no copy); long-run rounds are executed by the producer from its registers
+  uint16_t itot[32];         // inclusive prefix sum of ins + cpy: this command's output ends at round start + itot
+  uint16_t iins[32];         // inclusive prefix sum of ins: its literals end at literal index iins of the round
 };
 struct PageCtl {             // hand-over state of the two warps of a page (read after, written before a barrier)
   uint32_t produced, consumed;   // rounds published by the producer / retired by the consumer
@@ -101,7 +101,7 @@ struct WarpSmem {
   uint8_t sorted_lit[bgx::kNumLitSymbols];
   HuffAux aux[3];
   uint32_t lenlut[48];              // [0..23] insert code, [24..47] copy code: base | extra_bits << 16
-  alignas(16) uint32_t scratch[160]; // table build: cnt[16], next[16], 18 code-length-code lengths;
+  alignas(16) uint32_t scratch[96];  // table build: cnt[16], next[16], 18 code-length-code lengths;
                                     // decode: [0..31] insert table, [32..159] copy table (uint4)
   uint8_t litq[kLitQ];              // literal ring, indexed by page-global literal index
   alignas(16) uint8_t ring[kRing];  // output ring; while tables are read: code lengths [0..727] and the
@@ -545,7 +545,7 @@ BGX_DEV_NOINLINE PageResult decode_page_cta(const PageJob& job, WarpSmem* sm) {
   uint32_t lit_tail = 0;       // literals decoded so far
   uint32_t lit_head_p = 0;     // literals that the rounds produced so far consume
   uint32_t head_prev = 0;      // ... before the most recently produced round (it may still be unconsumed)
-  uint32_t s_ins = 0, s_cpy = 0, s_n = 0, s_mine = 0, s_round_ins = 0;   // a slow round waiting to be executed
+  uint32_t s_ins = 0, s_cpy = 0, s_n = 0, s_mine = 0, s_round_out = 0;   // a slow round waiting to be executed
   bool pdone = false;
   // ---------------- consumer state
   uint32_t pos = 0;            // bytes of the page produced so far
@@ -743,11 +743,11 @@ BGX_DEV_NOINLINE PageResult decode_page_cta(const PageJob& job, WarpSmem* sm) {
         }
         // ---- positions: one 64-bit warp scan gives every command its output and literal offsets
         const uint64_t incl_both = warp_incl_scan64(((uint64_t)(ins + cpy) << 32) | ins, lane);
-        rb->ins[lane] = ins;
-        rb->cpy[lane] = cpy;
+        rb->ins[lane] = (uint16_t)ins;
+        rb->cpy[lane] = (uint16_t)cpy;
         rb->dx[lane] = dx;            // final distance
-        rb->itot[lane] = (uint32_t)(incl_both >> 32);
-        rb->iins[lane] = (uint32_t)incl_both;
+        rb->itot[lane] = (uint16_t)(incl_both >> 32);
+        rb->iins[lane] = (uint16_t)incl_both;
         // ---- literals of this round (PageDecoder.cpp:196-206)
         const uint32_t round_ins = __shfl_sync(kFull, (uint32_t)incl_both, 31);
         const uint32_t round_out = __shfl_sync(kFull, (uint32_t)(incl_both >> 32), 31);
@@ -765,7 +765,7 @@ BGX_DEV_NOINLINE PageResult decode_page_cta(const PageJob& job, WarpSmem* sm) {
           head_prev = lit_head_p;
           lit_head_p += round_ins;
         } else {
-          s_ins = ins; s_cpy = cpy; s_n = n; s_mine = mine; s_round_ins = round_ins;
+          s_ins = ins; s_cpy = cpy; s_n = n; s_mine = mine; s_round_out = round_out;
         }
         if (lane == 0) {
           ctl->rflags[P & 1u] = (pdone ? 1u : 0u) | (fast ? 0u : 2u);
@@ -778,11 +778,12 @@ BGX_DEV_NOINLINE PageResult decode_page_cta(const PageJob& job, WarpSmem* sm) {
         RoundBuf* rb = &sm->rb[C & 1u];
         uint32_t p = ctl->pos;
         uint32_t lh = lit_head_p;
-        uint32_t err = 0;
-        for (uint32_t k = 0; k < s_n; ++k) {
+        uint32_t err = s_round_out > out_size - p ? (uint32_t)kPageErrOverrun : 0u;
+        for (uint32_t k = 0; k < s_n && !err; ++k) {
           uint32_t n_ins = __shfl_sync(kFull, s_ins, (int)k);
           const uint32_t n_cpy = __shfl_sync(kFull, s_cpy, (int)k);
           const uint32_t d_k = rb->dx[k];
+          if (n_cpy && (d_k == 0 || d_k > p + n_ins)) { err = kPageErrDistance; break; }
           while (n_ins) {
             uint32_t have = lit_tail - lh;
             if (have == 0) {
@@ -863,9 +864,9 @@ BGX_DEV_NOINLINE PageResult decode_page_cta(const PageJob& job, WarpSmem* sm) {
         const uint32_t round_ins = rb->iins[31];
         const uint32_t o_ins = pos + incl_tot - tot;        // where this command's literals go
         const uint32_t o_cpy = o_ins + ins;                 // where its copy goes
-        if (round_out > out_size - pos) err = kPageErrOverrun;
         const uint32_t round_end = pos + round_out;
-        {
+        if (!(rflags & 2u)) {   // (long-run rounds do not fit the 16-bit fields; the producer validates them itself)
+          if (round_out > out_size - pos) err = kPageErrOverrun;
           const uint32_t baddist = __ballot_sync(kFull, has_copy && (dist == 0 || dist > o_cpy));
           if (baddist && !err) err = kPageErrDistance;
         }
