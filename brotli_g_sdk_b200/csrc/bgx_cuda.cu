@@ -50,11 +50,13 @@ __global__ void __launch_bounds__(kPageThreads) bgx_decode_pages_kernel(const St
   __shared__ bgxk::WarpSmem sm;
   __shared__ uint32_t q_shared;
   const uint32_t tid = threadIdx.x;
+  if (tid == 0) q_shared = atomicAdd(&ctl->next_page, 1u);
   for (;;) {
-    if (tid == 0) q_shared = atomicAdd(&ctl->next_page, 1u);
     __syncthreads();
     const uint32_t q = q_begin + q_shared;   // [q_begin, q_end): the slice of the flat page queue this launch owns
     if (q >= q_end) break;
+    uint32_t q_next = 0;
+    if (tid == 0) q_next = atomicAdd(&ctl->next_page, 1u);   // claim the next page now: the atomic's latency hides behind this page
     // stream owning queue slot q: last stream with first_q <= q
     uint32_t lo = 0, hi = nstreams;
     while (hi - lo > 1) {
@@ -97,15 +99,23 @@ __global__ void __launch_bounds__(kPageThreads) bgx_decode_pages_kernel(const St
       page_status[q] = status;
       if (status & 0xffffu) atomicAdd(&ctl->bad_pages, 1u);
     }
-    __syncthreads();   // q_shared and the page arena are reused by the next page
+    __syncthreads();   // everybody is done with q_shared and the page arena
+    if (tid == 0) q_shared = q_next;
   }
 }
 
-// one thread per texture block: gather the block's fields from the planes, write the block
-__global__ void __launch_bounds__(256) bgx_decondition_kernel(const PreconLayout* __restrict__ layout,
-                                                              const uint8_t* __restrict__ planes, uint8_t* tex) {
-  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < layout->total_blocks) bgxk::decondition_block(*layout, t, planes, tex);
+struct PreconDev {          // one pre-conditioned stream of a launch
+  const PreconLayout* layout;
+  const uint8_t* planes;    // conditioned scratch planes (what the page kernel wrote)
+  uint8_t* tex;             // the caller's output
+};
+
+// one thread per texture block (blockIdx.y = stream): gather the block's fields from the planes, write the block
+__global__ void __launch_bounds__(256) bgx_decondition_kernel(const PreconDev* __restrict__ jobs) {
+  const PreconDev j = jobs[blockIdx.y];
+  const uint32_t total = j.layout->total_blocks;
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x)
+    bgxk::decondition_block(*j.layout, t, j.planes, j.tex);
 }
 
 }  // namespace
@@ -143,6 +153,7 @@ struct bgx_plan {
   uint32_t total_pages = 0;
   std::vector<PreconJob> precon;
   uint8_t* d_scratch = nullptr;   // backing store of all conditioned scratch planes
+  PreconDev* d_precon = nullptr;  // device copy of the pre-conditioned jobs, in stream order
   bgx_plan_info info{};
   cudaStream_t last_stream = nullptr;
   std::vector<uint32_t> q_start;  // [n+1]: first queue slot of caller stream i (prefix sum of its page count)
@@ -245,6 +256,7 @@ void bgx_plan_destroy(bgx_plan* plan) {
   if (plan->d_ctl) cudaFree(plan->d_ctl);
   if (plan->d_status) cudaFree(plan->d_status);
   if (plan->d_scratch) cudaFree(plan->d_scratch);
+  if (plan->d_precon) cudaFree(plan->d_precon);
   for (auto& p : plan->precon)
     if (p.d_layout) cudaFree(p.d_layout);
   delete plan;
@@ -336,10 +348,14 @@ int bgx_plan_create(bgx_context* ctx, const bgx_stream* streams, uint32_t n, bgx
         d.allow_delta = 1;
       }
     }
+    std::vector<PreconDev> hj;
     for (auto& p : plan->precon) {
       BGX_CUDA(ctx, cudaMalloc(&p.d_layout, sizeof(PreconLayout)));
       BGX_CUDA(ctx, cudaMemcpy(p.d_layout, &p.layout, sizeof(PreconLayout), cudaMemcpyHostToDevice));
+      hj.push_back(PreconDev{p.d_layout, p.d_planes, p.d_tex});
     }
+    BGX_CUDA(ctx, cudaMalloc(&plan->d_precon, hj.size() * sizeof(PreconDev)));
+    BGX_CUDA(ctx, cudaMemcpy(plan->d_precon, hj.data(), hj.size() * sizeof(PreconDev), cudaMemcpyHostToDevice));
   }
   const size_t ns = std::max<size_t>(plan->h_streams.size(), 1);
   BGX_CUDA(ctx, cudaMalloc(&plan->d_streams, ns * sizeof(StreamDev)));
@@ -347,7 +363,7 @@ int bgx_plan_create(bgx_context* ctx, const bgx_stream* streams, uint32_t n, bgx
     BGX_CUDA(ctx, cudaMemcpy(plan->d_streams, plan->h_streams.data(), plan->h_streams.size() * sizeof(StreamDev), cudaMemcpyHostToDevice));
   BGX_CUDA(ctx, cudaMalloc(&plan->d_ctl, kMaxGroups * sizeof(QueueCtl)));
   BGX_CUDA(ctx, cudaMalloc(&plan->d_status, std::max<size_t>(plan->total_pages, 1) * sizeof(uint32_t)));
-  plan->info.kernels_per_launch = (plan->total_pages ? 1u : 0u) + (uint32_t)plan->precon.size();
+  plan->info.kernels_per_launch = (plan->total_pages ? 1u : 0u) + (plan->precon.empty() ? 0u : 1u);
   plan->info.sm_count = (uint32_t)ctx->sm_count;
   plan->info.block_threads = kPageThreads;
   plan->info.smem_bytes_per_block = (uint32_t)sizeof(bgxk::WarpSmem);
@@ -372,10 +388,19 @@ static int launch_range(bgx_context* ctx, bgx_plan* plan, uint32_t a, uint32_t b
                                                  plan->d_ctl + group, plan->d_status);
     BGX_CUDA(ctx, cudaGetLastError());
   }
-  for (auto& p : plan->precon) {
+  // all pre-conditioned streams of the range in ONE launch (they are contiguous in plan->precon: stream order)
+  size_t j0 = plan->precon.size(), j1 = 0;
+  uint32_t max_blocks = 0;
+  for (size_t k = 0; k < plan->precon.size(); ++k) {
+    const PreconJob& p = plan->precon[k];
     if (p.stream_index < a || p.stream_index >= b) continue;
-    const uint32_t blocks = (p.layout.total_blocks + 255u) / 256u;
-    if (blocks) bgx_decondition_kernel<<<blocks, 256, 0, st>>>(p.d_layout, p.d_planes, p.d_tex);
+    j0 = std::min(j0, k);
+    j1 = std::max(j1, k + 1);
+    max_blocks = std::max(max_blocks, (p.layout.total_blocks + 255u) / 256u);
+  }
+  if (j1 > j0 && max_blocks) {
+    const dim3 grid(std::min<uint32_t>(max_blocks, 4096u), (uint32_t)(j1 - j0));
+    bgx_decondition_kernel<<<grid, 256, 0, st>>>(plan->d_precon + j0);
     BGX_CUDA(ctx, cudaGetLastError());
   }
   return bgx::kOk;

@@ -41,6 +41,10 @@
 #define BGX_DEV_NOINLINE inline
 #endif
 
+#ifndef BGX_RAW_PATH
+#define BGX_RAW_PATH 1
+#endif
+
 namespace bgxk {
 
 #ifdef BGX_STATS   // emulator-only instrumentation (never defined in the CUDA build)
@@ -1124,22 +1128,50 @@ BGX_DEV void copy_page_warp(uint8_t* dst, const uint8_t* src, uint32_t n) {
     }
     for (; v < nv; v += 32) d[v] = s[v];
     i = nv << 4;
+#if BGX_RAW_PATH == 1
+  } else if (((a & 15u) == 0) && ((b & 7u) == 0)) {
+    // typical stream layout: page data sits 8 bytes off a 16-byte boundary (8-byte header + 4n-byte table):
+    // two 8-byte loads per 16-byte store, 8 stores in flight per lane
+    const uint2* s = reinterpret_cast<const uint2*>(src);
+    uint4* d = reinterpret_cast<uint4*>(dst);
+    const uint32_t nv = n >> 4;
+    uint32_t v = lane;
+    for (; v + 7 * 32 < nv; v += 8 * 32) {
+      uint2 t[16];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { t[2 * u] = s[2 * (v + u * 32)]; t[2 * u + 1] = s[2 * (v + u * 32) + 1]; }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        uint4 w;
+        w.x = t[2 * u].x; w.y = t[2 * u].y; w.z = t[2 * u + 1].x; w.w = t[2 * u + 1].y;
+        d[v + u * 32] = w;
+      }
+    }
+    for (; v < nv; v += 32) {
+      const uint2 lo = s[2 * v], hi = s[2 * v + 1];
+      uint4 w;
+      w.x = lo.x; w.y = lo.y; w.z = hi.x; w.w = hi.y;
+      d[v] = w;
+    }
+    i = nv << 4;
+#else
   } else if (((a | b) & 7u) == 0) {
     // typical stream layout: page data sits 8 bytes off a 16-byte boundary (8-byte header + 4n-byte table):
-    // copy in coalesced 8-byte units, 8 loads in flight per lane
+    // copy in coalesced 8-byte units, 16 loads in flight per lane
     const uint2* s = reinterpret_cast<const uint2*>(src);
     uint2* d = reinterpret_cast<uint2*>(dst);
     const uint32_t nv = n >> 3;
     uint32_t v = lane;
-    for (; v + 7 * 32 < nv; v += 8 * 32) {
-      uint2 t[8];
+    for (; v + 15 * 32 < nv; v += 16 * 32) {
+      uint2 t[16];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) t[u] = s[v + u * 32];
+      for (int u = 0; u < 16; ++u) t[u] = s[v + u * 32];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) d[v + u * 32] = t[u];
+      for (int u = 0; u < 16; ++u) d[v + u * 32] = t[u];
     }
     for (; v < nv; v += 32) d[v] = s[v];
     i = nv << 3;
+#endif
   } else if (((a | b) & 3u) == 0) {
     const uint32_t* s = reinterpret_cast<const uint32_t*>(src);
     uint32_t* d = reinterpret_cast<uint32_t*>(dst);
