@@ -264,6 +264,11 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; brotli_g_sdk_b200 has no CPU decode path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    # Everything that is not the JSON line goes to stderr: NCCL prints its version banner on stdout when the
+    # first communicator is created, and the contract is ONE JSON line on stdout.
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     import brotli_g_sdk_b200 as sdk
@@ -411,7 +416,10 @@ def run_ours(args):
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
             "secondary": secondary, "bit_exact": True,
         }
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
 
