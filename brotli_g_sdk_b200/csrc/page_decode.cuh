@@ -916,8 +916,8 @@ BGX_DEV_NOINLINE PageResult decode_page_cta(const PageJob& job, WarpSmem* sm) {
               before += __popc(M);
               ord = ord < ilast ? ord : ilast;
               const uint32_t base = lds_u32(tab_a + 4u * ord);
-              const uint32_t v = lds_u8(litq_a + ((lit_head + t) & (kLitQ - 1)));
-              if (t < round_ins) sts_u8(ring_a + ((base + t) & (kRing - 1)), v);
+              if (t < round_ins)   // (lanes past the round's last literal must not touch slots the producer is filling)
+                sts_u8(ring_a + ((base + t) & (kRing - 1)), lds_u8(litq_a + ((lit_head + t) & (kLitQ - 1))));
             }
           }
           __syncwarp();

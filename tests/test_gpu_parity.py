@@ -159,3 +159,46 @@ def test_page_size_sweep_small_single_page_streams(sdk, oracle, dec):
     for d, o, s in zip(sources, outs, streams):
         assert np.array_equal(o, d)
     assert np.array_equal(oracle.decode(streams[7]), sources[7])
+
+
+def test_plan_rejects_bad_buffers(sdk, dec):
+    """device-resident contract: 16-byte aligned stream pointer, capacity covering the stream rounded up to 16"""
+    import torch
+    s = sdk.Encode(np.arange(100000, dtype=np.uint8))
+    t_in = torch.zeros(len(s) + 80, dtype=torch.uint8, device="cuda")
+    t_in[1: 1 + len(s)] = torch.from_numpy(s).cuda()
+    t_out = torch.zeros(100000, dtype=torch.uint8, device="cuda")
+    with pytest.raises(sdk.BrotligError) as e:
+        dec.plan([dict(d_src=t_in.data_ptr() + 1, src_size=len(s), src_capacity=len(s) + 64, d_dst=t_out.data_ptr(), dst_capacity=100000,
+                       header=bytes(s[:16]))])
+    assert e.value.code == 16 and "aligned" in str(e.value)
+    with pytest.raises(sdk.BrotligError) as e:
+        dec.plan([dict(d_src=t_in.data_ptr(), src_size=len(s), src_capacity=len(s), d_dst=t_out.data_ptr(), dst_capacity=100000,
+                       header=bytes(s[:16]))] if len(s) % 16 else [dict(d_src=t_in.data_ptr(), src_size=len(s), src_capacity=len(s) - 1,
+                                                                        d_dst=t_out.data_ptr(), dst_capacity=100000, header=bytes(s[:16]))])
+    assert e.value.code in (14, 16)
+    with pytest.raises(sdk.BrotligError):
+        dec.plan([dict(d_src=t_in.data_ptr(), src_size=len(s), src_capacity=len(s) + 64, d_dst=t_out.data_ptr(), dst_capacity=999,
+                       header=bytes(s[:16]))])
+
+
+def test_cli_round_trip(tmp_path, sdk):
+    """python -m brotli_g_sdk_b200.cli: compress a file, decompress the .brotlig on the GPU (twin of brotlig_cli)"""
+    import subprocess
+    import sys
+    from brotli_g_sdk_b200 import datagen
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "payload.bin"
+    data = datagen.mixed(700000, seed=3)
+    data.tofile(src)
+    env = dict(os.environ, PYTHONPATH=root)
+    r = subprocess.run([sys.executable, "-m", "brotli_g_sdk_b200.cli", "-pagesize", "65536", str(src)], capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stderr
+    comp = tmp_path / "payload.bin.brotlig"
+    assert comp.exists() and comp.stat().st_size < len(data)
+    out = tmp_path / "restored.bin"
+    r = subprocess.run([sys.executable, "-m", "brotli_g_sdk_b200.cli", "-num-repeat", "2", "-output", str(out), str(comp)],
+                       capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stderr
+    assert "GB/s decompressed" in r.stdout
+    assert np.array_equal(np.fromfile(out, dtype=np.uint8), data)
