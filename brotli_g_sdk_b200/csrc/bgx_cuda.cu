@@ -111,11 +111,36 @@ struct PreconDev {          // one pre-conditioned stream of a launch
 };
 
 // one thread per texture block (blockIdx.y = stream): gather the block's fields from the planes, write the block
+template <int FMT>
+__device__ __forceinline__ void decondition_stream_fast(const PreconLayout& L, const uint8_t* planes, uint8_t* tex) {
+  const uint32_t total = L.total_blocks;
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x)
+    bgxk::decondition_block_fast<FMT>(L, t, planes, tex);
+}
+
 __global__ void __launch_bounds__(256) bgx_decondition_kernel(const PreconDev* __restrict__ jobs) {
   const PreconDev j = jobs[blockIdx.y];
-  const uint32_t total = j.layout->total_blocks;
+  const PreconLayout& L = *j.layout;
+  // vector path: planes on a 8-byte boundary, every block of every mip on a block_bytes boundary
+  bool aligned = ((reinterpret_cast<uintptr_t>(j.planes) & 7u) == 0) &&
+                 ((reinterpret_cast<uintptr_t>(j.tex) & (L.block_bytes - 1u)) == 0);
+  for (uint32_t m = 0; m < L.num_mips; ++m)
+    aligned = aligned && ((L.mip_off_bytes[m] | L.pitch_bytes[m]) & (L.block_bytes - 1u)) == 0;
+  // (plane starts are multiples of total_blocks; 8-byte fields additionally need an 8-aligned plane start, which
+  //  holds for BC2's first plane at offset 0)
+  if (aligned) {
+    switch (L.format) {
+      case 1: decondition_stream_fast<1>(L, j.planes, j.tex); return;
+      case 2: decondition_stream_fast<2>(L, j.planes, j.tex); return;
+      case 3: decondition_stream_fast<3>(L, j.planes, j.tex); return;
+      case 4: decondition_stream_fast<4>(L, j.planes, j.tex); return;
+      case 5: decondition_stream_fast<5>(L, j.planes, j.tex); return;
+      default: break;
+    }
+  }
+  const uint32_t total = L.total_blocks;
   for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x)
-    bgxk::decondition_block(*j.layout, t, j.planes, j.tex);
+    bgxk::decondition_block(L, t, j.planes, j.tex);
 }
 
 }  // namespace

@@ -1083,8 +1083,8 @@ BGX_DEV void delta_decode_warp(uint8_t* page, uint32_t page_start, uint32_t page
   }
 }
 
-// Gathers block `t` (index in conditioned plane order over all mips) and writes it to the texture.
-BGX_HD void decondition_block(const bgx::PreconLayout& L, uint32_t t, const uint8_t* planes, uint8_t* tex) {
+// Texture byte offset of block `t` (index in conditioned plane order over all mips).
+BGX_HD uint32_t block_texture_offset(const bgx::PreconLayout& L, uint32_t t) {
   uint32_t mip = 0;
   while (mip + 1 < L.num_mips && t >= L.mip_off_blocks[mip + 1]) ++mip;
   const uint32_t block = t - L.mip_off_blocks[mip];
@@ -1100,12 +1100,60 @@ BGX_HD void decondition_block(const bgx::PreconLayout& L, uint32_t t, const uint
       col = 2u * (grp % gpr) + (in_grp & 1u);
     }
   }
-  uint8_t* dst = tex + L.mip_off_bytes[mip] + row * L.pitch_bytes[mip] + col * L.block_bytes;
+  return L.mip_off_bytes[mip] + row * L.pitch_bytes[mip] + col * L.block_bytes;
+}
+
+// Gathers block `t` from the planes and writes it to the texture, byte by byte (any alignment).
+BGX_HD void decondition_block(const bgx::PreconLayout& L, uint32_t t, const uint8_t* planes, uint8_t* tex) {
+  uint8_t* dst = tex + block_texture_offset(L, t);
   for (uint32_t sub = 0; sub < L.num_sub; ++sub) {
     const uint32_t sz = L.sub_size[sub];
     const uint8_t* src = planes + L.sub_stream_off[sub] + t * sz;
     for (uint32_t k = 0; k < sz; ++k) dst[L.sub_off[sub] + k] = src[k];
   }
+}
+
+// Same, for 4-byte aligned plane buffers and block-aligned texture rows: the field layout of the
+// format is a compile-time constant, so a block is assembled in registers from the widest loads each
+// field allows (every even-sized field starts on an even offset of an even-based plane) and leaves as
+// one 8- or 16-byte store.
+template <int FMT> struct BcFields;
+//                                 field sizes, one hex digit each, first field in the lowest digit
+template <> struct BcFields<1> { static constexpr int n = 3, bytes = 8;  static constexpr uint32_t sizes = 0x422u; };
+template <> struct BcFields<2> { static constexpr int n = 4, bytes = 16; static constexpr uint32_t sizes = 0x4228u; };
+template <> struct BcFields<3> { static constexpr int n = 6, bytes = 16; static constexpr uint32_t sizes = 0x422611u; };
+template <> struct BcFields<4> { static constexpr int n = 3, bytes = 8;  static constexpr uint32_t sizes = 0x611u; };
+template <> struct BcFields<5> { static constexpr int n = 6, bytes = 16; static constexpr uint32_t sizes = 0x611611u; };
+
+template <int FMT>
+BGX_DEV void decondition_block_fast(const bgx::PreconLayout& L, uint32_t t, const uint8_t* planes, uint8_t* tex) {
+  using F = BcFields<FMT>;
+  uint32_t w[4] = {0u, 0u, 0u, 0u};
+  int pos = 0;
+#pragma unroll
+  for (int sub = 0; sub < F::n; ++sub) {
+    const int sz = (int)((F::sizes >> (4 * sub)) & 15u);
+    const uint8_t* src = planes + L.sub_stream_off[sub] + t * (uint32_t)sz;
+    if (sz == 1) {
+      w[pos >> 2] |= (uint32_t)*src << (8 * (pos & 3));
+    } else if (sz == 4 && (pos & 3) == 0) {
+      w[pos >> 2] = *reinterpret_cast<const uint32_t*>(src);
+    } else if (sz == 8 && (pos & 3) == 0) {
+      const uint2 q = *reinterpret_cast<const uint2*>(src);
+      w[pos >> 2] = q.x;
+      w[(pos >> 2) + 1] = q.y;
+    } else {   // even size on an even position: 16-bit granules
+#pragma unroll
+      for (int k = 0; k < sz; k += 2) {
+        const int p = pos + k;
+        w[p >> 2] |= (uint32_t)*reinterpret_cast<const uint16_t*>(src + k) << (8 * (p & 3));
+      }
+    }
+    pos += sz;
+  }
+  uint8_t* dst = tex + block_texture_offset(L, t);
+  if (F::bytes == 8) *reinterpret_cast<uint2*>(dst) = make_uint2(w[0], w[1]);
+  else *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
 }
 
 // ---------------------------------------------------------------------------------------------
