@@ -81,19 +81,16 @@ struct HuffAux {
   uint16_t base[16];    // base[L]  = offset_in_sorted[L] - first_code[L]   (mod 2^16)
 };
 
-struct RoundBuf {            // one round of <= 32 commands, producer -> consumer
-  uint32_t dx[32];           // resolved match distance
-  uint16_t ins[32];          // 16-bit fields: only rounds of <= kRoundMax bytes are handed over through them
-  uint16_t cpy[32];          // (0 = no copy); long-run rounds are executed by the producer from its registers
-  uint16_t itot[32];         // inclusive prefix sum of ins + cpy: this command's output ends at round start + itot
-  uint16_t iins[32];         // inclusive prefix sum of ins: its literals end at literal index iins of the round
+constexpr uint32_t kQ = 4;   // rounds in flight between the producer and the consumer warp (power of two)
+struct RoundBuf {            // one round of <= 32 commands, producer -> consumer (only rounds of <= kRoundMax bytes;
+  uint32_t dx[32];           //   resolved match distance              long-run rounds stay in the producer's registers)
+  uint32_t pk[32];           //   inclusive prefix sums over the commands: bytes produced | literals consumed << 16
 };
-struct PageCtl {             // hand-over state of the two warps of a page (read after, written before a barrier)
-  uint32_t produced, consumed;   // rounds published by the producer / retired by the consumer
-  uint32_t slow;                 // 0 none, 1 a slow round was published, 2 consumer is ready for the producer to run it
+struct PageCtl {             // hand-over state of the two warps of a page (ordered by the named barriers)
   uint32_t pos, lit_head;        // page position / literal index across a slow round
-  uint32_t finished, err, is_delta;
-  uint32_t rflags[2];            // per RoundBuf: bit 0 = last round of the page, bit 1 = slow round
+  uint32_t err, is_delta;
+  uint32_t rflags[kQ];           // per RoundBuf: kFlagLast | kFlagSlow | kFlagAbort
+  uint32_t phead[kQ];            // producer only: literal head at the start of the round in that slot
 };
 
 struct WarpSmem {
@@ -110,24 +107,53 @@ struct WarpSmem {
   uint8_t litq[kLitQ];              // literal ring, indexed by page-global literal index
   alignas(16) uint8_t ring[kRing];  // output ring; while tables are read: code lengths [0..727] and the
                                     // 512 x u16 code-length-code LUT [1024..2047]
-  alignas(16) uint4 stage[4][32];   // compressed-input staging: 4 slots x 16 B per lane (cp.async ring)
-  RoundBuf rb[2];
+  alignas(16) uint4 stage[32][4];   // compressed-input staging: per lane 4 slots x 16 B (cp.async ring)
+  RoundBuf rb[kQ];
+  alignas(8) uint64_t mbar[2 * kQ];   // full[kQ], empty[kQ]
   PageCtl ctl;
 };
 
 // ---------------------------------------------------------------------------------------------
+// Explicit shared-state-space accesses. A `saddr_t` is a 32-bit shared-window address on the device (so
+// the hot loops issue plain `LDS/STS [R+imm]` instead of re-deriving the generic address of the arena for
+// every access) and a host pointer in the emulator.
+#ifdef BGX_EMULATED
+typedef uintptr_t saddr_t;
+BGX_DEV saddr_t saddr(const void* p) { return reinterpret_cast<uintptr_t>(p); }
+BGX_DEV uint32_t lds_u8(saddr_t a) { return *reinterpret_cast<const uint8_t*>(a); }
+BGX_DEV void sts_u8(saddr_t a, uint32_t v) { *reinterpret_cast<uint8_t*>(a) = (uint8_t)v; }
+BGX_DEV uint32_t lds_u32(saddr_t a) { return *reinterpret_cast<const uint32_t*>(a); }
+BGX_DEV uint2 lds_u32x2(saddr_t a) { return *reinterpret_cast<const uint2*>(a); }
+BGX_DEV uint32_t ldg_u8(const uint8_t* p) { return *p; }
+#else
+typedef uint32_t saddr_t;
+BGX_DEV saddr_t saddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+BGX_DEV uint32_t lds_u8(saddr_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+BGX_DEV void sts_u8(saddr_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+BGX_DEV uint32_t lds_u32(saddr_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+BGX_DEV uint2 lds_u32x2(saddr_t a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
+BGX_DEV uint32_t ldg_u8(const uint8_t* p) { uint32_t v; asm volatile("ld.global.u8 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
+#endif
+
+// ---------------------------------------------------------------------------------------------
 // Input staging + bit reader. Every lane reads its own sub-stream strictly sequentially, so the
 // compressed bytes are streamed through a small per-lane ring in shared memory: 4 slots x 16 B,
-// filled with cp.async (LDGSTS: global -> shared without registers) two to three slots AHEAD of
+// filled with cp.async (LDGSTS: global -> shared without registers) up to three slots AHEAD of
 // the read position. A lane therefore never waits on an HBM/L2 round trip in the middle of a
-// dependent decode chain; a refill is one LDS. Chunk indices are clamped to the stream buffer, so
-// the deliberate over-read of the format (BrotligDeswizzler.h:74-81) never leaves it.
-BGX_DEV void cp_async16(void* smem_dst, const void* gmem_src) {
+// dependent decode chain; a window refill is one predicated LDS. Chunk indices are clamped to the
+// stream buffer, so the deliberate over-read of the format (BrotligDeswizzler.h:74-81) never leaves it.
+//
+// The ring is topped up at a few explicit places (br_topup: once per round before the commands, once per
+// literal pair, once per code-length symbol), not inside every refill. Invariant: after a top-up at word
+// index k, chunks up to (k >> 2) + 3 are requested; a request waits for all EARLIER requests first. As
+// long as a lane fetches at most 4 words between two top-ups (a command with every extra field is
+// <= 102 bits, a literal pair <= 30), each chunk has landed one top-up before its first word is read,
+// and a chunk is only overwritten after its last word went into the window.
+BGX_DEV void cp_async16(saddr_t smem_dst, const void* gmem_src) {
 #ifdef BGX_EMULATED
-  memcpy(smem_dst, gmem_src, 16);
+  memcpy(reinterpret_cast<void*>(smem_dst), gmem_src, 16);
 #else
-  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem_src) : "memory");
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_dst), "l"(gmem_src) : "memory");
 #endif
 }
 BGX_DEV void cp_async_commit() {
@@ -145,7 +171,7 @@ BGX_DEV void cp_async_wait() {
 struct BitRd {
   uint32_t w0, w1, nxt;   // 64-bit window {w1:w0} and the prefetched next word
   uint32_t bitpos;        // < 32 between operations
-  uint32_t k;             // index (from the lane's first 16-byte chunk) of the next word to fetch
+  uint32_t k4;            // 4 x index (from the lane's first 16-byte chunk) of the next word to fetch
 };
 
 struct PageIn {
@@ -156,26 +182,37 @@ struct PageIn {
   const uint4* g16;       // 16-byte aligned address at or below the page start
   uint32_t lim16;         // largest chunk index that may be loaded through `g16`
   uint32_t c0;            // chunk index (relative to g16) of this lane's chunk 0
-  uint4* stage;           // &WarpSmem::stage[0][lane]; slot s is stage[s * 32]
+  saddr_t stage_a;        // this lane's 64-byte staging area (4 slots x 16 B)
+  uint32_t swz;           // slot swizzle ((lane >> 1) & 3) << 4: spreads the lanes' slots over the banks
+  uint32_t issued;        // chunks requested so far
+#ifdef BGX_EMULATED
+  uint32_t landed;        // emulator only: chunks known to have arrived (checks the top-up invariant)
+#endif
 };
 
 BGX_DEV uint32_t ld_word(const PageIn& in, uint32_t idx) { return in.base[idx < in.lim ? idx : in.lim]; }
 
 BGX_DEV void stage_issue(const PageIn& in, uint32_t chunk) {   // chunk: index from the lane's chunk 0
   const uint32_t g = in.c0 + chunk;
-  cp_async16(in.stage + (chunk & 3u) * 32u, in.g16 + (g < in.lim16 ? g : in.lim16));
+  cp_async16(in.stage_a + (((chunk << 4) ^ in.swz) & 0x30u), in.g16 + (g < in.lim16 ? g : in.lim16));
   cp_async_commit();
 }
-// Fetches word k of the lane's stream. When that was the last word of a chunk, the chunk three
-// ahead is requested into the slot of the chunk BEFORE this one (whose words were consumed long
-// ago), and the next chunk is guaranteed to have landed (at most 2 younger groups stay pending).
-BGX_DEV uint32_t stage_word(const PageIn& in, uint32_t k) {
-  const uint32_t v = reinterpret_cast<const uint32_t*>(in.stage + ((k >> 2) & 3u) * 32u)[k & 3u];
-  if ((k & 3u) == 3u) {
-    stage_issue(in, (k >> 2) + 3u);
-    cp_async_wait<2>();
+// Requests the chunks the reader may need before the next top-up (see the invariant above).
+BGX_DEV void br_topup(const BitRd& r, PageIn& in) {
+  while (in.issued < (r.k4 >> 4) + 4u) {
+    cp_async_wait<0>();
+#ifdef BGX_EMULATED
+    in.landed = in.issued;
+#endif
+    stage_issue(in, in.issued);
+    ++in.issued;
   }
-  return v;
+}
+BGX_DEV uint32_t stage_word(const PageIn& in, uint32_t k4) {
+#ifdef BGX_EMULATED
+  if ((k4 >> 4) >= in.landed) { fprintf(stderr, "bit reader: word %u read before its chunk landed (%u landed)\n", k4 >> 2, in.landed); abort(); }
+#endif
+  return lds_u32(in.stage_a + ((k4 ^ in.swz) & 0x3cu));
 }
 
 BGX_DEV void br_init(BitRd& r, PageIn& in, uint32_t byte_off) {
@@ -185,13 +222,19 @@ BGX_DEV void br_init(BitRd& r, PageIn& in, uint32_t byte_off) {
   stage_issue(in, 0);
   stage_issue(in, 1);
   stage_issue(in, 2);
+  stage_issue(in, 3);
+  in.issued = 4;
   cp_async_wait<0>();
+#ifdef BGX_EMULATED
+  in.landed = 4;
+#endif
   const uint32_t k0 = (rel & 15u) >> 2;
-  r.w0 = stage_word(in, k0);
-  r.w1 = stage_word(in, k0 + 1);
-  r.nxt = stage_word(in, k0 + 2);
-  r.k = k0 + 3;
+  r.w0 = stage_word(in, 4u * k0);
+  r.w1 = stage_word(in, 4u * k0 + 4u);
+  r.nxt = stage_word(in, 4u * k0 + 8u);
+  r.k4 = 4u * k0 + 12u;
   r.bitpos = (rel & 3u) * 8u;
+  br_topup(r, in);
 }
 BGX_DEV uint32_t br_peek(const BitRd& r) { return __funnelshift_r(r.w0, r.w1, r.bitpos); }  // 32 valid bits
 BGX_DEV void br_skip(BitRd& r, const PageIn& in, uint32_t n) {   // n <= 32
@@ -199,8 +242,8 @@ BGX_DEV void br_skip(BitRd& r, const PageIn& in, uint32_t n) {   // n <= 32
   if (r.bitpos >= 32u) {
     r.w0 = r.w1;
     r.w1 = r.nxt;
-    r.nxt = stage_word(in, r.k);
-    r.k += 1;
+    r.nxt = stage_word(in, r.k4);
+    r.k4 += 4u;
     r.bitpos -= 32u;
   }
 }
@@ -339,9 +382,10 @@ BGX_DEV void build_table(WarpSmem* sm, const uint8_t* lens, uint32_t n, uint16_t
 // Reads one prefix-code description (trivial / simple / complex) and builds its tables.
 // Returns 0 or kPageErrTable. Cursor conventions: every table starts at sub-stream 0 (lane 0).
 template <int BITS, typename SortedT>
-BGX_DEV uint32_t load_table(WarpSmem* sm, BitRd& rd, const PageIn& in, uint32_t alphabet, uint16_t* lut, HuffAux& aux,
+BGX_DEV uint32_t load_table(WarpSmem* sm, BitRd& rd, PageIn& in, uint32_t alphabet, uint16_t* lut, HuffAux& aux,
                             SortedT* sorted, uint32_t lane) {
   const uint32_t max_bits = bgx::bit_length(alphabet - 1);
+  br_topup(rd, in);
   uint32_t hdr = 0;
   if (lane == 0) hdr = br_read(rd, in, 6);
   hdr = __shfl_sync(kFull, hdr, 0);
@@ -415,6 +459,7 @@ BGX_DEV uint32_t load_table(WarpSmem* sm, BitRd& rd, const PageIn& in, uint32_t 
   uint8_t* lens = sm->ring;
   uint32_t filled = 0, prev_carry = bgx::kInitialRepeatLen;
   while (filled < alphabet) {
+    br_topup(rd, in);
     const uint32_t pk = br_peek(rd);
     const uint32_t e = cl_lut[pk & 511u];
     const uint32_t s = e & 0xffu, l = e >> 8;
@@ -444,28 +489,6 @@ BGX_DEV uint32_t load_table(WarpSmem* sm, BitRd& rd, const PageIn& in, uint32_t 
 
 
 // ---------------------------------------------------------------------------------------------
-// Explicit shared-state-space accesses for the hot assembly loops. A `saddr_t` is a 32-bit
-// shared-window address on the device (so the loops issue plain `LDS/STS [R+imm]` instead of
-// re-deriving the generic address of the arena for every access) and a host pointer in the emulator.
-#ifdef BGX_EMULATED
-typedef uintptr_t saddr_t;
-BGX_DEV saddr_t saddr(const void* p) { return reinterpret_cast<uintptr_t>(p); }
-BGX_DEV uint32_t lds_u8(saddr_t a) { return *reinterpret_cast<const uint8_t*>(a); }
-BGX_DEV void sts_u8(saddr_t a, uint32_t v) { *reinterpret_cast<uint8_t*>(a) = (uint8_t)v; }
-BGX_DEV uint32_t lds_u32(saddr_t a) { return *reinterpret_cast<const uint32_t*>(a); }
-BGX_DEV uint2 lds_u32x2(saddr_t a) { return *reinterpret_cast<const uint2*>(a); }
-BGX_DEV uint32_t ldg_u8(const uint8_t* p) { return *p; }
-#else
-typedef uint32_t saddr_t;
-BGX_DEV saddr_t saddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-BGX_DEV uint32_t lds_u8(saddr_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
-BGX_DEV void sts_u8(saddr_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
-BGX_DEV uint32_t lds_u32(saddr_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
-BGX_DEV uint2 lds_u32x2(saddr_t a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
-BGX_DEV uint32_t ldg_u8(const uint8_t* p) { uint32_t v; asm volatile("ld.global.u8 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
-#endif
-
-// ---------------------------------------------------------------------------------------------
 struct PageJob {
   const uint8_t* in;        // compressed page (4-byte aligned)
   uint32_t in_size;
@@ -492,549 +515,643 @@ BGX_DEV void flush_bytes(const WarpSmem* sm, uint8_t* out, uint32_t from, uint32
 
 // Decodes `cnt` literals in this lane (lane-dependent count allowed) into the literal ring at
 // page-global literal indices tail + j*32 + lane.
-BGX_DEV void decode_literals(WarpSmem* sm, BitRd& rd, const PageIn& in, uint32_t tail, uint32_t cnt, uint32_t lane) {
+BGX_DEV void decode_literals(WarpSmem* sm, BitRd& rd, PageIn& in, uint32_t tail, uint32_t cnt, uint32_t lane) {
+  const saddr_t litq_a = saddr(sm->litq);
   uint32_t q = (tail + lane) & (kLitQ - 1);
-  uint32_t j = 0;
-  // two literals per 32-bit peek (2 x 15 bits at most): one window refill check per pair
-  for (; j + 2 <= cnt; j += 2) {
+  // two literals per 32-bit peek (2 x 15 bits at most): one window refill check per pair. An odd count ends
+  // with a pair whose second half is neither stored nor consumed.
+#pragma unroll 1
+  for (uint32_t j = 0; j < cnt; j += 2) {
+    br_topup(rd, in);
     const uint32_t pk = br_peek(rd);
     uint32_t len1, len2;
     const uint32_t s1 = huff_decode<kLitLutBits>(sm->lut_lit, sm->aux[2], sm->sorted_lit, bgx::kNumLitSymbols, pk, len1);
     const uint32_t s2 = huff_decode<kLitLutBits>(sm->lut_lit, sm->aux[2], sm->sorted_lit, bgx::kNumLitSymbols, pk >> len1, len2);
-    sm->litq[q] = (uint8_t)s1;
-    sm->litq[(q + 32) & (kLitQ - 1)] = (uint8_t)s2;
-    q = (q + 64) & (kLitQ - 1);
-    br_skip(rd, in, len1 + len2);
-  }
-  if (j < cnt) {
-    uint32_t len;
-    const uint32_t sym = huff_decode<kLitLutBits>(sm->lut_lit, sm->aux[2], sm->sorted_lit, bgx::kNumLitSymbols,
-                                                  br_peek(rd), len);
-    sm->litq[q] = (uint8_t)sym;
-    br_skip(rd, in, len);
+    const bool two = j + 1u < cnt;
+    sts_u8(litq_a + q, s1);
+    if (two) sts_u8(litq_a + ((q + 32u) & (kLitQ - 1)), s2);
+    q = (q + 64u) & (kLitQ - 1);
+    br_skip(rd, in, two ? len1 + len2 : len1);
   }
 }
 
 // The page decoder: a CTA of TWO warps decodes one page as a two-stage pipeline over rounds.
 //   warp 0, the PRODUCER: owns the 32 bit readers; reads the tables, decodes each round's commands
-//           and literals (everything that consumes bits) and publishes them in a RoundBuf;
-//   warp 1, the CONSUMER: resolves the distance ring, places literals and match copies in the output
-//           ring and streams the page to HBM.
-// One __syncthreads() per iteration hands a round over (double buffered), so the serial dependency
-// chain of a page is split in two halves that run concurrently and the SM holds twice the warps
-// for the same shared-memory footprint. Rounds with long runs ("slow") are executed by the producer
-// straight to global memory after the consumer has resolved their distances and flushed its ring.
-// All threads of the CTA call this with identical arguments.
-BGX_DEV_NOINLINE PageResult decode_page_cta(const PageJob& job, WarpSmem* sm) {
-  const uint32_t lane = lane_id();
-  const uint32_t warp = warp_index();
-  const uint32_t lt_mask = (1u << lane) - 1u;
-  const uint32_t le_mask = 0xffffffffu >> (31u - lane);
-  PageCtl* ctl = &sm->ctl;
-  PageResult res;
-  res.status = kPageOk;
-  res.is_delta = 0;
-#ifndef BGX_EMULATED
-  __builtin_assume(__isGlobal(job.out));
-  __builtin_assume(__isGlobal(job.in));
+//           and literals (everything that consumes bits), resolves the distance ring and publishes the
+//           round in a RoundBuf;
+//   warp 1, the CONSUMER: places literals and match copies in the output ring and streams the page to HBM.
+// The two roles are separate loops (each warp only keeps its own state in registers). Rounds travel
+// through a ring of kQ RoundBufs guarded by named CTA barriers (PTX bar.sync / bar.arrive), so that
+// neither warp polls and the producer may run up to kQ rounds ahead:
+//   full[q]   the producer ARRIVES after publishing round r (q = r mod kQ); the consumer SYNCs before reading it
+//   empty[q]  the consumer ARRIVES once it no longer needs the round's RoundBuf and literals; the producer
+//             SYNCs on it before it reuses the slot (and earlier, when the literal ring is short of room)
+//   slow      two rendezvous around a round with long runs ("slow"), which the producer executes straight
+//             to global memory after the consumer has flushed its ring.
+// Every barrier phase is matched (one arrive per sync) so that all barriers are idle again when the page
+// is done -- the CTA is persistent and decodes many pages.
+constexpr uint32_t kBarSlow = 1u;   // named CTA barrier (bar.sync 1, 64) for the slow-round rendezvous; 0 is __syncthreads
+constexpr uint32_t kPageThreadsDev = 64u;
+enum : uint32_t { kFlagLast = 1u, kFlagSlow = 2u, kFlagAbort = 4u };
+
+BGX_DEV void bar_sync_slow() {
+#ifdef BGX_EMULATED
+  wemu::named_bar_sync((int)kBarSlow, (int)kPageThreadsDev);
+#else
+  asm volatile("bar.sync %0, %1;" ::"n"(kBarSlow), "n"(kPageThreadsDev) : "memory");
 #endif
+}
+// full[] / empty[] are mbarriers in shared memory (no per-SM resource besides 8 bytes each): one elected lane
+// arrives (release) after a __syncwarp, every lane of the waiting warp observes the phase (acquire). Round j
+// uses phase j / kQ of slot j mod kQ, so the parity to wait for is (j / kQ) & 1.
+BGX_DEV void mbar_init(saddr_t a, uint32_t count) {
+#ifdef BGX_EMULATED
+  wemu::mbar_init(reinterpret_cast<uint64_t*>(a), count);
+#else
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
+#endif
+}
+BGX_DEV void mbar_init_fence() {
+#ifndef BGX_EMULATED
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#endif
+}
+BGX_DEV void mbar_arrive(saddr_t a) {
+#ifdef BGX_EMULATED
+  wemu::mbar_arrive(reinterpret_cast<uint64_t*>(a));
+#else
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(a) : "memory");
+#endif
+}
+BGX_DEV void mbar_wait(saddr_t a, uint32_t parity) {
+#ifdef BGX_EMULATED
+  wemu::mbar_wait(reinterpret_cast<uint64_t*>(a), parity);
+#else
+  asm volatile(
+      "{\n\t.reg .pred p;\n"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n\t}" ::"r"(a), "r"(parity) : "memory");
+#endif
+}
+// the whole warp signals: its earlier shared-memory accesses are ordered before the elected lane's arrive
+BGX_DEV void warp_arrive(saddr_t a, uint32_t lane) {
+  __syncwarp();
+  if (lane == 0) mbar_arrive(a);
+}
+BGX_DEV uint32_t ld_volatile_u32(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
+
+// ------------------------------------------------------------------------------------- PRODUCER
+BGX_DEV void producer_warp(const PageJob& job, WarpSmem* sm) {
+  const uint32_t lane = lane_id();
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  PageCtl* ctl = &sm->ctl;
   uint8_t* const out = job.out;
   const uint32_t out_size = job.out_size;
 
-  // ---------------- producer state
   PageIn in;
   BitRd rd;
-  rd.w0 = rd.w1 = rd.nxt = rd.bitpos = rd.k = 0;
   uint32_t npostfix = 0, ndirect = 0;
+  if (lane == 0) {
+    ctl->pos = 0; ctl->lit_head = 0; ctl->is_delta = 0;
+  }
+  in.base = reinterpret_cast<const uint32_t*>(job.in);
+  in.lim = (job.in_limit >> 2) ? (job.in_limit >> 2) - 1 : 0;
+  {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(job.in);
+    in.g16 = reinterpret_cast<const uint4*>(a & ~(uintptr_t)15);
+    const uint32_t span = (uint32_t)(a & 15u) + job.in_limit;       // bytes readable from g16
+    in.lim16 = (span >> 4) ? (span >> 4) - 1 : 0;
+    in.c0 = 0;
+    in.stage_a = saddr(&sm->stage[lane][0]);
+    in.swz = ((lane >> 1) & 3u) << 4;
+    in.issued = 0;
+  }
+  // ---- length-code tables (RFC 7932 section 5)
+  if (lane < 24) {
+    sm->lenlut[lane] = bgx::insert_base(lane) | (bgx::insert_extra_bits(lane) << 16);
+    sm->lenlut[24 + lane] = bgx::copy_base(lane) | (bgx::copy_extra_bits(lane) << 16);
+  }
+  // ---- page header + sub-stream size table (PageDecoder.cpp:79-121): every lane parses the header
+  //      words it needs itself (they are the first few words of the page: broadcast loads)
+  uint32_t sub_off;
+  {
+    auto hdr_bits = [&](uint32_t hpos, uint32_t n) -> uint32_t {   // n <= 25
+      const uint32_t w = hpos >> 5, b = hpos & 31u;
+      const uint32_t lo = ld_word(in, w), hi = ld_word(in, w + 1);
+      return __funnelshift_r(lo, hi, b) & low_mask(n);
+    };
+    npostfix = hdr_bits(0, 2);
+    ndirect = hdr_bits(2, 4) << npostfix;
+    const uint32_t is_delta = (hdr_bits(6, 1) && job.allow_delta) ? 1u : 0u;
+    if (lane == 0) ctl->is_delta = is_delta;
+    const uint32_t base_bits = bgx::floor_log2((job.in_size + 31u) / 32u) + 1u;
+    const uint32_t dbits_bits = bgx::floor_log2(bgx::floor_log2(job.in_size - 1u) + 1u) + 1u;
+    const uint32_t base_size = hdr_bits(8, base_bits);
+    const uint32_t delta_bits = hdr_bits(8 + base_bits, dbits_bits);
+    const uint32_t tbl = 8 + base_bits + dbits_bits;
+    const uint32_t hdr_bytes = ((tbl + 32u * delta_bits + 31u) / 32u) * 4u;
+    const uint32_t dmine = delta_bits ? hdr_bits(tbl + lane * delta_bits, delta_bits > 25 ? 25 : delta_bits) : 0u;
+    const uint32_t mysize = base_size + dmine;
+    sub_off = hdr_bytes + warp_incl_scan(mysize, lane) - mysize;
+  }
+  br_init(rd, in, sub_off);
+  __syncwarp();
+  // ---- the three prefix codes: insert&copy (728), distance (544), literal (256)  (PageDecoder.cpp:126-147)
+  uint32_t terr = load_table<kCmdLutBits>(sm, rd, in, bgx::kNumCmdSymbols, sm->lut_cmd, sm->aux[0], sm->sorted_cmd, lane);
+  if (!terr) terr = load_table<kDistLutBits>(sm, rd, in, bgx::kNumDistSymbols, sm->lut_dist, sm->aux[1], sm->sorted_dist, lane);
+  if (!terr) terr = load_table<kLitLutBits>(sm, rd, in, bgx::kNumLitSymbols, sm->lut_lit, sm->aux[2], sm->sorted_lit, lane);
+  __syncwarp();
+  if (terr && lane == 0) ctl->err = terr;
+  __syncwarp();
+
+  const saddr_t full_a = saddr(sm->mbar), empty_a = full_a + 8u * kQ;
+  uint32_t rnd = 0;            // rounds published so far
+  uint32_t synced = 0;         // empty[] phases taken so far: rounds < synced are known to be consumed
   uint32_t lit_tail = 0;       // literals decoded so far
-  uint32_t lit_head_p = 0;     // literals that the rounds produced so far consume
-  uint32_t head_prev = 0;      // ... before the most recently produced round (it may still be unconsumed)
-  uint32_t s_ins = 0, s_cpy = 0, s_n = 0, s_mine = 0, s_round_out = 0;   // a slow round waiting to be executed
+  uint32_t lit_head_p = 0;     // literals that the rounds published so far consume
+  uint32_t r0 = 4, r1 = 11, r2 = 15, r3 = 16;   // distance ring (PageDecoder.cpp:150-153)
   bool pdone = false;
-  // ---------------- consumer state
+  for (;;) {
+    const uint32_t q = rnd & (kQ - 1u);
+    while (synced + kQ <= rnd) {   // slot q still holds round rnd - kQ: wait until the consumer is done with it
+      mbar_wait(empty_a + 8u * (synced & (kQ - 1u)), (synced / kQ) & 1u);
+      ++synced;
+    }
+    if (ld_volatile_u32(&ctl->err)) {   // a table error, or the consumer rejected a round: tell it to stop
+      if (lane == 0) ctl->rflags[q] = kFlagAbort;
+      warp_arrive(full_a + 8u * q, lane);
+      break;
+    }
+    RoundBuf* rb = &sm->rb[q];
+    br_topup(rd, in);
+    // ---- one command per lane, speculatively (lanes after the sentinel roll back)
+    BitRd r = rd;
+    uint32_t len;
+    const uint32_t pk = br_peek(r);
+    uint32_t sym = huff_decode<kCmdLutBits>(sm->lut_cmd, sm->aux[0], sm->sorted_cmd, bgx::kNumCmdSymbols, pk, len);
+    const uint32_t sent = __ballot_sync(kFull, sym == (uint32_t)bgx::kCmdSentinel);
+    const uint32_t n = sent ? (uint32_t)(__ffs((int)sent) - 1) : 32u;   // commands in this round
+    pdone = sent != 0;
+    uint32_t ins = 0, cpy = 0, dx = 0;   // dx: explicit distance, or 0x80000000 | short code 0..15
+    if (lane < n) {
+      uint32_t ic, cc = 0;
+      bool has_copy = false;
+      if (sym < (uint32_t)bgx::kCmdSentinel) {
+        ic = bgx::icp_insert_code(sym);
+        cc = bgx::icp_copy_code(sym);
+        has_copy = true;
+      } else {
+        ic = sym - (uint32_t)bgx::kCmdSentinel;      // insert-only (PageDecoder.cpp:308-317)
+        if (ic > 23u) ic = 23u;
+      }
+      const uint32_t ei = sm->lenlut[ic];
+      const uint32_t ec = has_copy ? sm->lenlut[24 + cc] : 0u;
+      const uint32_t nbi = ei >> 16, nbc = ec >> 16;
+      if (len + nbi + nbc <= 32u) {   // symbol + both extra-bit fields out of the one 32-bit peek
+        ins = (ei & 0xffffu) + (shr32(pk, len) & low_mask(nbi));
+        cpy = (ec & 0xffffu) + (shr32(pk, len + nbi) & low_mask(nbc));
+        br_skip(r, in, len + nbi + nbc);
+      } else {                        // 24-bit extras: field by field
+        br_skip(r, in, len);
+        ins = (ei & 0xffffu) + br_read(r, in, nbi);
+        cpy = (ec & 0xffffu) + br_read(r, in, nbc);
+      }
+      if (has_copy) {
+        dx = 0x80000000u;             // implicit "last distance" (symbol < 128, PageDecoder.cpp:305)
+        if (sym >= 128u) {
+          const uint32_t pk2 = br_peek(r);
+          const uint32_t dcode = huff_decode<kDistLutBits>(sm->lut_dist, sm->aux[1], sm->sorted_dist, bgx::kNumDistSymbols, pk2, len);
+          if (dcode >= 16u + ndirect) {   // explicit distance with extra bits (PageDecoder.cpp:376-394)
+            const uint32_t v = dcode - ndirect - 16u;
+            uint32_t nb = 1u + (v >> (npostfix + 1u));
+            if (nb > 24u) nb = 24u;
+            uint32_t extra;
+            if (len + nb <= 32u) {
+              extra = shr32(pk2, len) & low_mask(nb);
+              br_skip(r, in, len + nb);
+            } else {
+              br_skip(r, in, len);
+              extra = br_read(r, in, nb);
+            }
+            const uint32_t h = v >> npostfix, lo = v & ((1u << npostfix) - 1u);
+            dx = (((((2u + (h & 1u)) << nb) - 4u + extra) << npostfix) + lo + ndirect + 1u) & 0x7fffffffu;
+          } else {
+            br_skip(r, in, len);
+            dx = dcode >= 16u ? dcode - 15u : (0x80000000u | dcode);   // direct codes (PageDecoder.cpp:369-373) / ring codes
+          }
+        }
+      } else {
+        cpy = 0;
+      }
+      rd = r;
+    } else if (lane == n) {
+      br_skip(r, in, len);
+      rd = r;   // the sentinel's code bits are consumed; its lane then continues with literals
+    }
+    // ---- distance ring, resolved by relaxation (PageDecoder.cpp:345-404)
+    {
+      const bool has_copy = cpy != 0;
+      const uint32_t dcode = (dx >> 31) ? (dx & 0xffu) : 16u;   // 16 = explicit distance
+      uint32_t dist = (dx >> 31) ? 0u : dx;
+      const uint32_t push = __ballot_sync(kFull, has_copy && dcode != 0);   // commands that enter the ring
+      const uint32_t any_short = __ballot_sync(kFull, has_copy && dcode < 16u);
+      if (any_short) {
+      const uint32_t below = push & lt_mask;
+      bool unresolved = has_copy && dcode < 16u;
+      uint32_t slot = 0;       // which ring slot (0..3) the short code refers to, and the offset applied to it
+      int32_t delta = 0;
+      if (unresolved) {
+        if (dcode < 4u) slot = dcode;
+        else {
+          const uint32_t c = dcode - 4u;              // 0..11
+          slot = c >= 6u ? 1u : 0u;
+          const uint32_t k = c >= 6u ? c - 6u : c;    // 0..5 => -1 +1 -2 +2 -3 +3
+          delta = (int32_t)(k >> 1) + 1;
+          if (!(k & 1u)) delta = -delta;
+        }
+      }
+      // source: the slot-th most recent pusher below me, else the carried ring
+      uint32_t b = below;
+      for (uint32_t k = 0; k < slot && b; ++k) b &= ~(1u << (31 - __clz((int)b)));
+      const uint32_t npush_below = __popc(below);
+      const bool from_carry = slot >= npush_below;
+      const uint32_t src_lane = from_carry ? 0u : (uint32_t)(31 - __clz((int)b));
+      const uint32_t cslot = slot - (from_carry ? npush_below : 0u);
+      const uint32_t carry_val = cslot == 0 ? r0 : cslot == 1 ? r1 : cslot == 2 ? r2 : r3;
+      uint32_t resolved = __ballot_sync(kFull, !unresolved);
+      while (resolved != kFull) {
+        BGX_STAT(emu_stats().ring_iters++);
+        const uint32_t v = __shfl_sync(kFull, dist, src_lane);
+        const bool ready = unresolved && (from_carry || ((resolved >> src_lane) & 1u));
+        if (ready) {
+          dist = (uint32_t)((int32_t)(from_carry ? carry_val : v) + delta);
+          unresolved = false;
+        }
+        resolved = __ballot_sync(kFull, !unresolved);
+      }
+      }
+      if (push) {   // new carried ring = four most recent pushers of this round, then the old ring
+        uint32_t pb = push;
+        uint32_t nr[4];
+        uint32_t old_idx = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t hb = pb ? (uint32_t)(31 - __clz((int)pb)) : 0u;
+          const uint32_t v = __shfl_sync(kFull, dist, hb);
+          if (pb) { nr[k] = v; pb &= ~(1u << hb); }
+          else { nr[k] = old_idx == 0 ? r0 : old_idx == 1 ? r1 : old_idx == 2 ? r2 : r3; ++old_idx; }
+        }
+        r0 = nr[0]; r1 = nr[1]; r2 = nr[2]; r3 = nr[3];
+      }
+      dx = dist;
+    }
+    // ---- positions: one 64-bit warp scan gives every command its output and literal offsets
+    const uint64_t incl_both = warp_incl_scan64(((uint64_t)(ins + cpy) << 32) | ins, lane);
+    // ---- literals of this round (PageDecoder.cpp:196-206)
+    const uint32_t round_ins = __shfl_sync(kFull, (uint32_t)incl_both, 31);
+    const uint32_t round_out = __shfl_sync(kFull, (uint32_t)(incl_both >> 32), 31);
+    const uint32_t avail = lit_tail - lit_head_p;     // decoded ahead of need in earlier rounds (< 32)
+    const uint32_t need = round_ins > avail ? round_ins - avail : 0u;
+    const uint32_t mult = n ? (n == 32u ? (need + 31u) >> 5 : (need + n - 1u) / n) : 0u;
+    const uint32_t rl = n * mult;                     // literals the stream carries for this round
+    uint32_t mine = rl > lane ? (rl - lane + 31u) >> 5 : 0u;   // literal indices lit_tail + j*32 + lane
+    // the literal ring must hold this round's literals next to those of every round the consumer may still
+    // be working on: rounds >= synced. Take more empty[] phases while that helps.
+    uint32_t head_known = synced == rnd ? lit_head_p : ctl->phead[synced & (kQ - 1u)];
+    bool fits = (lit_tail - head_known) + rl <= kLitQ;
+    while (!fits && synced < rnd) {
+      mbar_wait(empty_a + 8u * (synced & (kQ - 1u)), (synced / kQ) & 1u);
+      ++synced;
+      head_known = synced == rnd ? lit_head_p : ctl->phead[synced & (kQ - 1u)];
+      fits = (lit_tail - head_known) + rl <= kLitQ;
+    }
+    const bool fast = round_out <= kRoundMax && fits;
+    BGX_STAT(emu_stats().rounds++; emu_stats().lits += rl; if (!fast) emu_stats().slow_rounds++);
+    if (lane == 0) ctl->phead[q] = lit_head_p;   // literal head at the start of this round
+    if (fast) {
+      decode_literals(sm, rd, in, lit_tail, mine, lane);
+      lit_tail += rl;
+      lit_head_p += round_ins;
+      rb->dx[lane] = dx;            // final distance
+      rb->pk[lane] = (uint32_t)(incl_both >> 32) | ((uint32_t)incl_both << 16);   // inclusive sums: output | literals << 16
+      if (lane == 0) ctl->rflags[q] = pdone ? kFlagLast : 0u;
+      warp_arrive(full_a + 8u * q, lane);
+    } else {
+      // ---- slow round (long runs): executed here, straight to global memory, command by command, once the
+      //      consumer has caught up, flushed its ring and published its position.
+      if (lane == 0) ctl->rflags[q] = kFlagSlow | (pdone ? kFlagLast : 0u);
+      warp_arrive(full_a + 8u * q, lane);
+      bar_sync_slow();
+      const uint32_t s_ins = ins, s_cpy = cpy, s_n = n, s_round_out = round_out;
+      uint32_t s_mine = mine;
+      uint32_t p = ctl->pos;
+      uint32_t lh = lit_head_p;
+      uint32_t err = ld_volatile_u32(&ctl->err);   // (the consumer may have rejected an earlier round)
+      if (!err && s_round_out > out_size - p) err = kPageErrOverrun;
+      for (uint32_t k = 0; k < s_n && !err; ++k) {
+        uint32_t n_ins = __shfl_sync(kFull, s_ins, (int)k);
+        const uint32_t n_cpy = __shfl_sync(kFull, s_cpy, (int)k);
+        const uint32_t d_k = __shfl_sync(kFull, dx, (int)k);
+        if (n_cpy && (d_k == 0 || d_k > p + n_ins)) { err = kPageErrDistance; break; }
+        while (n_ins) {
+          uint32_t have = lit_tail - lh;
+          if (have == 0) {
+            // decode the next chunk of this round's literals (as many as the literal ring takes)
+            const uint32_t room = kLitQ >> 5;
+            const uint32_t c = s_mine < room ? s_mine : room;
+            const uint32_t total = __reduce_add_sync(kFull, c);
+            if (total == 0) { err = kPageErrLiterals; break; }
+            decode_literals(sm, rd, in, lit_tail, c, lane);
+            s_mine -= c;
+            lit_tail += total;
+            __syncwarp();
+            have = lit_tail - lh;
+          }
+          const uint32_t take = n_ins < have ? n_ins : have;
+          for (uint32_t j = lane; j < take; j += 32) out[p + j] = sm->litq[(lh + j) & (kLitQ - 1)];
+          p += take;
+          lh += take;
+          n_ins -= take;
+          __syncwarp();
+        }
+        if (err) break;
+        if (n_cpy) {
+          const uint32_t s_k = p - d_k;
+          for (uint32_t j = lane; j < n_cpy; j += 32) {
+            const uint32_t m = j < d_k ? j : j % d_k;
+            out[p + j] = out[s_k + m];
+          }
+          p += n_cpy;
+          __syncwarp();
+        }
+      }
+      // literals the round still carries (decoded ahead of need, at most 31 remain unused)
+      while (!err && __reduce_add_sync(kFull, s_mine) != 0) {
+        const uint32_t room = (kLitQ - (lit_tail - lh)) >> 5;
+        const uint32_t c = s_mine < room ? s_mine : room;
+        const uint32_t total = __reduce_add_sync(kFull, c);
+        if (total == 0) { err = kPageErrLiterals; break; }
+        decode_literals(sm, rd, in, lit_tail, c, lane);
+        s_mine -= c;
+        lit_tail += total;
+        __syncwarp();
+      }
+      lit_head_p = lh;
+      if (lane == 0) {
+        ctl->pos = p;
+        ctl->lit_head = lh;
+        if (err) ctl->err = err;
+      }
+      bar_sync_slow();
+    }
+    ++rnd;
+    if (pdone) break;
+  }
+}
+
+// ------------------------------------------------------------------------------------- CONSUMER
+BGX_DEV void consumer_warp(const PageJob& job, WarpSmem* sm) {
+  const uint32_t lane = lane_id();
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  const uint32_t le_mask = 0xffffffffu >> (31u - lane);
+  PageCtl* ctl = &sm->ctl;
+  uint8_t* const out = job.out;
+  const uint32_t out_size = job.out_size;
   uint32_t pos = 0;            // bytes of the page produced so far
   uint32_t flushed = 0;        // bytes already in global memory
   int32_t ring_from = 0;       // ring holds valid data for positions >= ring_from (and > end - kRing)
   uint32_t lit_head = 0;       // page-global literal index of the next literal to place
-  uint32_t r0 = 4, r1 = 11, r2 = 15, r3 = 16;   // distance ring (PageDecoder.cpp:150-153)
-  bool await_slow = false, slow_was_last = false;
+  bool failed = false;         // a round was rejected: only keep the hand-over going until the producer stops
   const bool out_aligned = (reinterpret_cast<uintptr_t>(out) & 15u) == 0;
+  const saddr_t full_a = saddr(sm->mbar), empty_a = full_a + 8u * kQ;
 
-  if (warp == 0) {
-    if (lane == 0) {
-      ctl->produced = 0; ctl->consumed = 0; ctl->slow = 0; ctl->pos = 0; ctl->lit_head = 0;
-      ctl->finished = 0; ctl->err = 0; ctl->is_delta = 0;
+  for (uint32_t r = 0;; ++r) {
+    const uint32_t q = r & (kQ - 1u);
+    mbar_wait(full_a + 8u * q, (r / kQ) & 1u);
+    const uint32_t rflags = ctl->rflags[q];
+    if ((rflags & kFlagAbort) || failed) {
+      if (rflags & kFlagAbort) break;
+      if (rflags & kFlagSlow) { bar_sync_slow(); bar_sync_slow(); }   // the producer's rendezvous (it skips the work)
+      warp_arrive(empty_a + 8u * q, lane);
+      if (rflags & kFlagLast) break;
+      continue;
     }
-    in.base = reinterpret_cast<const uint32_t*>(job.in);
-    in.lim = (job.in_limit >> 2) ? (job.in_limit >> 2) - 1 : 0;
+    if (rflags & kFlagSlow) {
+      // ---- slow round: hand a fully flushed page over to the producer, pick it up again afterwards
+      flush_bytes(sm, out, flushed, pos, lane);
+      if (lane == 0) ctl->pos = pos;
+      bar_sync_slow();
+      bar_sync_slow();
+      pos = ctl->pos;
+      flushed = pos;
+      ring_from = (int32_t)pos;
+      lit_head = ctl->lit_head;
+      warp_arrive(empty_a + 8u * q, lane);
+      if (rflags & kFlagLast) {
+        for (uint32_t z = pos + lane; z < out_size; z += 32) out[z] = 0;
+        break;
+      }
+      continue;
+    }
+    const RoundBuf* rb = &sm->rb[q];
+    const uint32_t pk = rb->pk[lane];
+    const uint32_t dist = rb->dx[lane];            // resolved by the producer
+    const uint32_t pk_last = rb->pk[31];
+    uint32_t pk_prev = __shfl_up_sync(kFull, pk, 1);
+    if (lane == 0) pk_prev = 0;
+    const uint32_t incl_tot = pk & 0xffffu, incl_ins = pk >> 16;
+    const uint32_t tot = incl_tot - (pk_prev & 0xffffu);
+    const uint32_t ins = incl_ins - (pk_prev >> 16);
+    const uint32_t cpy = tot - ins;
+    const bool has_copy = cpy != 0;
+    const uint32_t round_out = pk_last & 0xffffu;
+    const uint32_t round_ins = pk_last >> 16;
+    const uint32_t o_ins = pos + incl_tot - tot;        // where this command's literals go
+    const uint32_t o_cpy = o_ins + ins;                 // where its copy goes
+    const uint32_t round_end = pos + round_out;
     {
-      const uintptr_t a = reinterpret_cast<uintptr_t>(job.in);
-      in.g16 = reinterpret_cast<const uint4*>(a & ~(uintptr_t)15);
-      const uint32_t span = (uint32_t)(a & 15u) + job.in_limit;       // bytes readable from g16
-      in.lim16 = (span >> 4) ? (span >> 4) - 1 : 0;
-      in.c0 = 0;
-      in.stage = &sm->stage[0][lane];
+      uint32_t err = 0;
+      if (round_out > out_size - pos) err = kPageErrOverrun;
+      const uint32_t baddist = __ballot_sync(kFull, has_copy && (dist == 0 || dist > o_cpy));
+      if (baddist && !err) err = kPageErrDistance;
+      if (err) {
+        if (lane == 0) ctl->err = err;
+        failed = true;
+        warp_arrive(empty_a + 8u * q, lane);
+        if (rflags & kFlagLast) break;
+        continue;
+      }
     }
-    // ---- length-code tables (RFC 7932 section 5)
-    if (lane < 24) {
-      sm->lenlut[lane] = bgx::insert_base(lane) | (bgx::insert_extra_bits(lane) << 16);
-      sm->lenlut[24 + lane] = bgx::copy_base(lane) | (bgx::copy_extra_bits(lane) << 16);
-    }
-    // ---- page header + sub-stream size table (PageDecoder.cpp:79-121): every lane parses the header
-    //      words it needs itself (they are the first few words of the page: broadcast loads)
-    uint32_t sub_off;
+    const uint32_t lq = incl_ins - ins;                // round-local index of this command's first literal
+    const int32_t ring_lo = ring_from > (int32_t)round_end - (int32_t)kRing ? ring_from : (int32_t)round_end - (int32_t)kRing;
+#ifdef BGX_STATS
     {
-      auto hdr_bits = [&](uint32_t hpos, uint32_t n) -> uint32_t {   // n <= 25
-        const uint32_t w = hpos >> 5, b = hpos & 31u;
-        const uint32_t lo = ld_word(in, w), hi = ld_word(in, w + 1);
-        return __funnelshift_r(lo, hi, b) & low_mask(n);
+      const uint32_t mi = __reduce_max_sync(kFull, ins < kCoopLen ? ins : 0u);
+      const uint32_t ncp = __popc(__ballot_sync(kFull, cpy != 0));
+      const uint32_t far = __reduce_add_sync(kFull, (cpy && dist > 1500u) ? cpy : 0u);
+      const uint32_t ov = __popc(__ballot_sync(kFull, cpy != 0 && dist < cpy));
+      BGX_STAT(emu_stats().sum_max_ins += mi; emu_stats().ins_bytes += round_ins; emu_stats().copies += ncp;
+               emu_stats().copy_bytes += round_out - round_ins; emu_stats().far_bytes += far; emu_stats().overlap_copies += ov);
+    }
+#endif
+    // ---- inserts, flattened: lane t places literal t of the round (perfectly balanced, any length).
+    //      Commands with literals are compacted into tab[]; a per-chunk bit mask of their first
+    //      literal index turns "which command owns literal t" into one popc.
+    uint32_t* tab = sm->scratch;                       // [32] (o_ins - first literal index)
+    const saddr_t ring_a = saddr(sm->ring), litq_a = saddr(sm->litq), tab_a = saddr(sm->scratch);
+    {
+      const uint32_t has = __ballot_sync(kFull, ins != 0);
+      if (ins) tab[__popc(has & lt_mask)] = o_ins - lq;
+      __syncwarp();
+      const uint32_t icidx = lq >> 5;
+      const uint32_t icbit = ins ? (1u << (lq & 31u)) : 0u;
+      const uint32_t ilast = __popc(has) - 1u;
+      uint32_t before = 0;
+      for (uint32_t c = 0, c0 = 0; c0 < round_ins; ++c, c0 += 32) {
+        const uint32_t M = __reduce_or_sync(kFull, icidx == c ? icbit : 0u);
+        const uint32_t t = c0 + lane;
+        uint32_t ord = before + __popc(M & le_mask) - 1u;
+        before += __popc(M);
+        ord = ord < ilast ? ord : ilast;
+        const uint32_t base = lds_u32(tab_a + 4u * ord);
+        if (t < round_ins)   // (lanes past the round's last literal must not touch slots the producer is filling)
+          sts_u8(ring_a + ((base + t) & (kRing - 1)), lds_u8(litq_a + ((lit_head + t) & (kLitQ - 1))));
+      }
+    }
+    warp_arrive(empty_a + 8u * q, lane);   // the RoundBuf and this round's literals are no longer needed
+    // ---- copies. Wavefront 1 (flattened, like the inserts): every copy whose source already is
+    //      final, i.e. lies below the destination of the first pending copy. Sources may be in
+    //      the ring or (far matches) in L1/L2.
+    const uint32_t src_hi = o_cpy - dist + (cpy < dist ? cpy : dist);  // one past the last distinct source byte
+    uint32_t pending = __ballot_sync(kFull, cpy != 0);
+    if (pending) {
+      const int first = __ffs((int)pending) - 1;
+      const uint32_t hwm = __shfl_sync(kFull, o_cpy, first);           // everything below is final
+      const bool ready1 = cpy != 0 && dist >= cpy && ((int)lane == first || src_hi <= hwm);
+      const uint32_t len1 = ready1 ? cpy : 0u;
+      const uint32_t E1 = warp_incl_scan(len1, lane);
+      const uint32_t T1 = __shfl_sync(kFull, E1, 31);
+      const uint32_t S1 = E1 - len1;
+      const uint32_t m1 = __ballot_sync(kFull, ready1);
+      uint2* tab2 = reinterpret_cast<uint2*>(sm->scratch + 32);        // [32] (dst - first flat index, distance)
+      if (ready1) tab2[__popc(m1 & lt_mask)] = make_uint2(o_cpy - S1, dist);
+      __syncwarp();
+      const uint32_t cidx = S1 >> 5;
+      const uint32_t cbit = ready1 ? (1u << (S1 & 31u)) : 0u;
+      const uint32_t last = __popc(m1) - 1u;
+      uint32_t before = 0;
+      const saddr_t tab2_a = tab_a + 128u;
+      // NU 32-byte chunks per trip; all loads of a trip are issued before its stores
+      auto trip = [&](auto nu_tag, uint32_t c, uint32_t c0) {
+        constexpr int NU = decltype(nu_tag)::value;
+        uint32_t M[NU];
+#pragma unroll
+        for (int u = 0; u < NU; ++u) M[u] = __reduce_or_sync(kFull, cidx == c + u ? cbit : 0u);
+        uint32_t d[NU];
+        uint32_t v[NU];
+#pragma unroll
+        for (int u = 0; u < NU; ++u) {
+          const uint32_t t = c0 + 32u * u + lane;
+          uint32_t ord = before + __popc(M[u] & le_mask) - 1u;
+          before += __popc(M[u]);
+          ord = ord < last ? ord : last;                               // lanes past the end read a valid entry
+          const uint2 q = lds_u32x2(tab2_a + 8u * ord);
+          d[u] = q.x + t;
+          const uint32_t sp = d[u] - q.y;
+          const bool ok = t < T1;
+          const bool near = (int32_t)sp >= ring_lo;
+          v[u] = 0;
+          if (ok && near) v[u] = lds_u8(ring_a + (sp & (kRing - 1)));
+          if (ok && !near) v[u] = ldg_u8(out + sp);
+          if (!ok) d[u] = 0xffffffffu;
+        }
+#pragma unroll
+        for (int u = 0; u < NU; ++u)
+          if (d[u] != 0xffffffffu) sts_u8(ring_a + (d[u] & (kRing - 1)), v[u]);
       };
-      npostfix = hdr_bits(0, 2);
-      ndirect = hdr_bits(2, 4) << npostfix;
-      const uint32_t is_delta = (hdr_bits(6, 1) && job.allow_delta) ? 1u : 0u;
-      if (lane == 0) ctl->is_delta = is_delta;
-      const uint32_t base_bits = bgx::floor_log2((job.in_size + 31u) / 32u) + 1u;
-      const uint32_t dbits_bits = bgx::floor_log2(bgx::floor_log2(job.in_size - 1u) + 1u) + 1u;
-      const uint32_t base_size = hdr_bits(8, base_bits);
-      const uint32_t delta_bits = hdr_bits(8 + base_bits, dbits_bits);
-      const uint32_t tbl = 8 + base_bits + dbits_bits;
-      const uint32_t hdr_bytes = ((tbl + 32u * delta_bits + 31u) / 32u) * 4u;
-      const uint32_t dmine = delta_bits ? hdr_bits(tbl + lane * delta_bits, delta_bits > 25 ? 25 : delta_bits) : 0u;
-      const uint32_t mysize = base_size + dmine;
-      sub_off = hdr_bytes + warp_incl_scan(mysize, lane) - mysize;
+      uint32_t c = 0, c0 = 0;
+      for (; c0 + 64u < T1; c += 4, c0 += 128) trip(std::integral_constant<int, 4>{}, c, c0);
+      if (c0 < T1) {
+        if (T1 - c0 > 32u) trip(std::integral_constant<int, 2>{}, c, c0);
+        else trip(std::integral_constant<int, 1>{}, c, c0);
+      }
+      __syncwarp();
+      pending &= ~m1;
     }
-    br_init(rd, in, sub_off);
-    __syncwarp();
-    // ---- the three prefix codes: insert&copy (728), distance (544), literal (256)  (PageDecoder.cpp:126-147)
-    uint32_t terr = load_table<kCmdLutBits>(sm, rd, in, bgx::kNumCmdSymbols, sm->lut_cmd, sm->aux[0], sm->sorted_cmd, lane);
-    if (!terr) terr = load_table<kDistLutBits>(sm, rd, in, bgx::kNumDistSymbols, sm->lut_dist, sm->aux[1], sm->sorted_dist, lane);
-    if (!terr) terr = load_table<kLitLutBits>(sm, rd, in, bgx::kNumLitSymbols, sm->lut_lit, sm->aux[2], sm->sorted_lit, lane);
-    if (terr && lane == 0) ctl->err = terr;
+    //      Remaining copies (dependent on this round's copies, or overlapping themselves): in command
+    //      order, each by the whole warp (lane j moves byte j; almost always a single step). In-order
+    //      execution satisfies every dependency; an overlapping copy (dist < len) repeats its
+    //      `dist`-byte pattern exactly as the byte-serial reference loop does (PageDecoder.cpp:222-232).
+    while (pending) {
+      const int k = __ffs((int)pending) - 1;
+      pending &= pending - 1;
+      const uint32_t n_k = __shfl_sync(kFull, cpy, k);
+      const uint32_t o_k = __shfl_sync(kFull, o_cpy, k);
+      const uint32_t d_k = __shfl_sync(kFull, dist, k);
+      BGX_STAT(emu_stats().wavefronts++; emu_stats().sum_max_cpy += n_k);
+      for (uint32_t j = lane; j < n_k; j += 32) {
+        const uint32_t m = j < d_k ? j : j % d_k;
+        const uint32_t sp = o_k - d_k + m;
+        const uint32_t v = ((int32_t)sp >= ring_lo) ? lds_u8(ring_a + (sp & (kRing - 1))) : ldg_u8(out + sp);
+        sts_u8(ring_a + ((o_k + j) & (kRing - 1)), v);
+      }
+      __syncwarp();
+    }
+    pos = round_end;
+    lit_head += round_ins;
+    // ---- write-combined flush of complete 512-byte chunks
+    if (pos - flushed >= kFlushChunk) {
+      if (out_aligned) {
+        if (flushed & 15u) {   // after a cooperative (direct) episode the flush point may be unaligned
+          const uint32_t to = (flushed + 15u) & ~15u;
+          flush_bytes(sm, out, flushed, to, lane);
+          flushed = to;
+        }
+        while (pos - flushed >= kFlushChunk) {
+          const uint32_t f = flushed + 16u * lane;
+          *reinterpret_cast<uint4*>(out + f) = *reinterpret_cast<const uint4*>(&sm->ring[f & (kRing - 1)]);
+          flushed += kFlushChunk;
+        }
+      } else {
+        const uint32_t to = flushed + ((pos - flushed) / kFlushChunk) * kFlushChunk;
+        flush_bytes(sm, out, flushed, to, lane);
+        flushed = to;
+      }
+      __syncwarp();
+    }
+    if (rflags & kFlagLast) {
+      // ---- last round: whatever is still only in the ring, then zero-fill (the reference memsets the page first)
+      flush_bytes(sm, out, flushed, pos, lane);
+      for (uint32_t z = pos + lane; z < out_size; z += 32) out[z] = 0;
+      break;
+    }
+  }
+}
+
+// All threads of the CTA call this with identical arguments.
+BGX_DEV_NOINLINE PageResult decode_page_cta(const PageJob& job, WarpSmem* sm) {
+#ifndef BGX_EMULATED
+  __builtin_assume(__isGlobal(job.out));
+  __builtin_assume(__isGlobal(job.in));
+#endif
+  if (warp_index() == 0 && lane_id() == 0) {
+    for (uint32_t i = 0; i < 2u * kQ; ++i) mbar_init(saddr(&sm->mbar[i]), 1u);
+    mbar_init_fence();
+    sm->ctl.err = 0;
   }
   __syncthreads();
-
-  for (;;) {
-    // snapshot of the hand-over state (written before the last barrier)
-    const uint32_t P = ctl->produced, C = ctl->consumed, S = ctl->slow;
-    const bool stop = ctl->finished || ctl->err;
-    __syncthreads();   // everybody holds the same snapshot before anybody updates it
-    if (stop) break;
-
-    if (warp == 0) {
-      // =============================================================== PRODUCER
-      if (S == 0 && !pdone && P - C < 2u) {
-        RoundBuf* rb = &sm->rb[P & 1u];
-        // ---- one command per lane, speculatively (lanes after the sentinel roll back)
-        BitRd r = rd;
-        uint32_t len;
-        const uint32_t pk = br_peek(r);
-        uint32_t sym = huff_decode<kCmdLutBits>(sm->lut_cmd, sm->aux[0], sm->sorted_cmd, bgx::kNumCmdSymbols, pk, len);
-        const uint32_t sent = __ballot_sync(kFull, sym == (uint32_t)bgx::kCmdSentinel);
-        const uint32_t n = sent ? (uint32_t)(__ffs((int)sent) - 1) : 32u;   // commands in this round
-        pdone = sent != 0;
-        uint32_t ins = 0, cpy = 0, dx = 0;   // dx: explicit distance, or 0x80000000 | short code 0..15
-        if (lane < n) {
-          uint32_t ic, cc = 0;
-          bool has_copy = false;
-          if (sym < (uint32_t)bgx::kCmdSentinel) {
-            ic = bgx::icp_insert_code(sym);
-            cc = bgx::icp_copy_code(sym);
-            has_copy = true;
-          } else {
-            ic = sym - (uint32_t)bgx::kCmdSentinel;      // insert-only (PageDecoder.cpp:308-317)
-            if (ic > 23u) ic = 23u;
-          }
-          const uint32_t ei = sm->lenlut[ic];
-          const uint32_t ec = has_copy ? sm->lenlut[24 + cc] : 0u;
-          const uint32_t nbi = ei >> 16, nbc = ec >> 16;
-          if (len + nbi + nbc <= 32u) {   // symbol + both extra-bit fields out of the one 32-bit peek
-            ins = (ei & 0xffffu) + (shr32(pk, len) & low_mask(nbi));
-            cpy = (ec & 0xffffu) + (shr32(pk, len + nbi) & low_mask(nbc));
-            br_skip(r, in, len + nbi + nbc);
-          } else {                        // 24-bit extras: field by field
-            br_skip(r, in, len);
-            ins = (ei & 0xffffu) + br_read(r, in, nbi);
-            cpy = (ec & 0xffffu) + br_read(r, in, nbc);
-          }
-          if (has_copy) {
-            dx = 0x80000000u;             // implicit "last distance" (symbol < 128, PageDecoder.cpp:305)
-            if (sym >= 128u) {
-              const uint32_t pk2 = br_peek(r);
-              const uint32_t dcode = huff_decode<kDistLutBits>(sm->lut_dist, sm->aux[1], sm->sorted_dist, bgx::kNumDistSymbols, pk2, len);
-              if (dcode >= 16u + ndirect) {   // explicit distance with extra bits (PageDecoder.cpp:376-394)
-                const uint32_t v = dcode - ndirect - 16u;
-                uint32_t nb = 1u + (v >> (npostfix + 1u));
-                if (nb > 24u) nb = 24u;
-                uint32_t extra;
-                if (len + nb <= 32u) {
-                  extra = shr32(pk2, len) & low_mask(nb);
-                  br_skip(r, in, len + nb);
-                } else {
-                  br_skip(r, in, len);
-                  extra = br_read(r, in, nb);
-                }
-                const uint32_t h = v >> npostfix, lo = v & ((1u << npostfix) - 1u);
-                dx = (((((2u + (h & 1u)) << nb) - 4u + extra) << npostfix) + lo + ndirect + 1u) & 0x7fffffffu;
-              } else {
-                br_skip(r, in, len);
-                dx = dcode >= 16u ? dcode - 15u : (0x80000000u | dcode);   // direct codes (PageDecoder.cpp:369-373) / ring codes
-              }
-            }
-          } else {
-            cpy = 0;
-          }
-          rd = r;
-        } else if (lane == n) {
-          br_skip(r, in, len);
-          rd = r;   // the sentinel's code bits are consumed; its lane then continues with literals
-        }
-        // ---- distance ring, resolved by relaxation (PageDecoder.cpp:345-404)
-        {
-          const bool has_copy = cpy != 0;
-          const uint32_t dcode = (dx >> 31) ? (dx & 0xffu) : 16u;   // 16 = explicit distance
-          uint32_t dist = (dx >> 31) ? 0u : dx;
-          const uint32_t push = __ballot_sync(kFull, has_copy && dcode != 0);   // commands that enter the ring
-          const uint32_t any_short = __ballot_sync(kFull, has_copy && dcode < 16u);
-          if (any_short) {
-          const uint32_t below = push & lt_mask;
-          bool unresolved = has_copy && dcode < 16u;
-          uint32_t slot = 0;       // which ring slot (0..3) the short code refers to, and the offset applied to it
-          int32_t delta = 0;
-          if (unresolved) {
-            if (dcode < 4u) slot = dcode;
-            else {
-              const uint32_t c = dcode - 4u;              // 0..11
-              slot = c >= 6u ? 1u : 0u;
-              const uint32_t k = c >= 6u ? c - 6u : c;    // 0..5 => -1 +1 -2 +2 -3 +3
-              delta = (int32_t)(k >> 1) + 1;
-              if (!(k & 1u)) delta = -delta;
-            }
-          }
-          // source: the slot-th most recent pusher below me, else the carried ring
-          uint32_t b = below;
-          for (uint32_t k = 0; k < slot && b; ++k) b &= ~(1u << (31 - __clz((int)b)));
-          const uint32_t npush_below = __popc(below);
-          const bool from_carry = slot >= npush_below;
-          const uint32_t src_lane = from_carry ? 0u : (uint32_t)(31 - __clz((int)b));
-          const uint32_t cslot = slot - (from_carry ? npush_below : 0u);
-          const uint32_t carry_val = cslot == 0 ? r0 : cslot == 1 ? r1 : cslot == 2 ? r2 : r3;
-          uint32_t resolved = __ballot_sync(kFull, !unresolved);
-          while (resolved != kFull) {
-            BGX_STAT(emu_stats().ring_iters++);
-            const uint32_t v = __shfl_sync(kFull, dist, src_lane);
-            const bool ready = unresolved && (from_carry || ((resolved >> src_lane) & 1u));
-            if (ready) {
-              dist = (uint32_t)((int32_t)(from_carry ? carry_val : v) + delta);
-              unresolved = false;
-            }
-            resolved = __ballot_sync(kFull, !unresolved);
-          }
-          }
-          if (push) {   // new carried ring = four most recent pushers of this round, then the old ring
-            uint32_t pb = push;
-            uint32_t nr[4];
-            uint32_t old_idx = 0;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint32_t hb = pb ? (uint32_t)(31 - __clz((int)pb)) : 0u;
-              const uint32_t v = __shfl_sync(kFull, dist, hb);
-              if (pb) { nr[k] = v; pb &= ~(1u << hb); }
-              else { nr[k] = old_idx == 0 ? r0 : old_idx == 1 ? r1 : old_idx == 2 ? r2 : r3; ++old_idx; }
-            }
-            r0 = nr[0]; r1 = nr[1]; r2 = nr[2]; r3 = nr[3];
-          }
-          dx = dist;
-        }
-        // ---- positions: one 64-bit warp scan gives every command its output and literal offsets
-        const uint64_t incl_both = warp_incl_scan64(((uint64_t)(ins + cpy) << 32) | ins, lane);
-        rb->ins[lane] = (uint16_t)ins;
-        rb->cpy[lane] = (uint16_t)cpy;
-        rb->dx[lane] = dx;            // final distance
-        rb->itot[lane] = (uint16_t)(incl_both >> 32);
-        rb->iins[lane] = (uint16_t)incl_both;
-        // ---- literals of this round (PageDecoder.cpp:196-206)
-        const uint32_t round_ins = __shfl_sync(kFull, (uint32_t)incl_both, 31);
-        const uint32_t round_out = __shfl_sync(kFull, (uint32_t)(incl_both >> 32), 31);
-        const uint32_t avail = lit_tail - lit_head_p;     // decoded ahead of need in earlier rounds (< 32)
-        const uint32_t need = round_ins > avail ? round_ins - avail : 0u;
-        const uint32_t mult = n ? (n == 32u ? (need + 31u) >> 5 : (need + n - 1u) / n) : 0u;
-        const uint32_t rl = n * mult;                     // literals the stream carries for this round
-        const uint32_t mine = rl > lane ? (rl - lane + 31u) >> 5 : 0u;   // literal indices lit_tail + j*32 + lane
-        // the literal ring must hold this round's literals next to those of the round the consumer still works on
-        const bool fast = round_out <= kRoundMax && (lit_tail - head_prev) + rl <= kLitQ;
-        BGX_STAT(emu_stats().rounds++; emu_stats().lits += rl; if (!fast) emu_stats().slow_rounds++);
-        if (fast) {
-          decode_literals(sm, rd, in, lit_tail, mine, lane);
-          lit_tail += rl;
-          head_prev = lit_head_p;
-          lit_head_p += round_ins;
-        } else {
-          s_ins = ins; s_cpy = cpy; s_n = n; s_mine = mine; s_round_out = round_out;
-        }
-        if (lane == 0) {
-          ctl->rflags[P & 1u] = (pdone ? 1u : 0u) | (fast ? 0u : 2u);
-          ctl->produced = P + 1u;
-          if (!fast) ctl->slow = 1u;
-        }
-      } else if (S == 2u) {
-        // ---- execute the slow round (long runs) straight to global memory, command by command.
-        //      The consumer has resolved the distances (rb->dx), flushed its ring and published pos.
-        RoundBuf* rb = &sm->rb[C & 1u];
-        uint32_t p = ctl->pos;
-        uint32_t lh = lit_head_p;
-        uint32_t err = s_round_out > out_size - p ? (uint32_t)kPageErrOverrun : 0u;
-        for (uint32_t k = 0; k < s_n && !err; ++k) {
-          uint32_t n_ins = __shfl_sync(kFull, s_ins, (int)k);
-          const uint32_t n_cpy = __shfl_sync(kFull, s_cpy, (int)k);
-          const uint32_t d_k = rb->dx[k];
-          if (n_cpy && (d_k == 0 || d_k > p + n_ins)) { err = kPageErrDistance; break; }
-          while (n_ins) {
-            uint32_t have = lit_tail - lh;
-            if (have == 0) {
-              // decode the next chunk of this round's literals (as many as the literal ring takes)
-              const uint32_t room = kLitQ >> 5;
-              const uint32_t c = s_mine < room ? s_mine : room;
-              const uint32_t total = __reduce_add_sync(kFull, c);
-              if (total == 0) { err = kPageErrLiterals; break; }
-              decode_literals(sm, rd, in, lit_tail, c, lane);
-              s_mine -= c;
-              lit_tail += total;
-              __syncwarp();
-              have = lit_tail - lh;
-            }
-            const uint32_t take = n_ins < have ? n_ins : have;
-            for (uint32_t j = lane; j < take; j += 32) out[p + j] = sm->litq[(lh + j) & (kLitQ - 1)];
-            p += take;
-            lh += take;
-            n_ins -= take;
-            __syncwarp();
-          }
-          if (err) break;
-          if (n_cpy) {
-            const uint32_t s_k = p - d_k;
-            for (uint32_t j = lane; j < n_cpy; j += 32) {
-              const uint32_t m = j < d_k ? j : j % d_k;
-              out[p + j] = out[s_k + m];
-            }
-            p += n_cpy;
-            __syncwarp();
-          }
-        }
-        // literals the round still carries (decoded ahead of need, at most 31 remain unused)
-        while (!err && __reduce_add_sync(kFull, s_mine) != 0) {
-          const uint32_t room = (kLitQ - (lit_tail - lh)) >> 5;
-          const uint32_t c = s_mine < room ? s_mine : room;
-          const uint32_t total = __reduce_add_sync(kFull, c);
-          if (total == 0) { err = kPageErrLiterals; break; }
-          decode_literals(sm, rd, in, lit_tail, c, lane);
-          s_mine -= c;
-          lit_tail += total;
-          __syncwarp();
-        }
-        lit_head_p = lh;
-        head_prev = lh;
-        if (lane == 0) {
-          ctl->pos = p;
-          ctl->lit_head = lh;
-          ctl->consumed = C + 1u;
-          ctl->slow = 0u;
-          if (err) ctl->err = err;
-        }
-      }
-    } else {
-      // =============================================================== CONSUMER
-      if (await_slow && S == 0u) {            // the producer has executed the slow round: pick the page up again
-        pos = ctl->pos;
-        flushed = pos;
-        ring_from = (int32_t)pos;
-        lit_head = ctl->lit_head;
-        await_slow = false;
-        if (slow_was_last) {
-          for (uint32_t q = pos + lane; q < out_size; q += 32) out[q] = 0;
-          if (lane == 0) ctl->finished = 1u;
-        }
-      } else if (S != 2u && C < P && !await_slow) {
-        RoundBuf* rb = &sm->rb[C & 1u];
-        const uint32_t rflags = ctl->rflags[C & 1u];
-        const uint32_t ins = rb->ins[lane], cpy = rb->cpy[lane], dx = rb->dx[lane];
-        const bool has_copy = cpy != 0;
-        const uint32_t dist = dx;            // resolved by the producer
-        uint32_t err = 0;
-        // ---- positions
-        const uint32_t tot = ins + cpy;
-        const uint32_t incl_tot = rb->itot[lane];
-        const uint32_t incl_ins = rb->iins[lane];
-        const uint32_t round_out = rb->itot[31];
-        const uint32_t round_ins = rb->iins[31];
-        const uint32_t o_ins = pos + incl_tot - tot;        // where this command's literals go
-        const uint32_t o_cpy = o_ins + ins;                 // where its copy goes
-        const uint32_t round_end = pos + round_out;
-        if (!(rflags & 2u)) {   // (long-run rounds do not fit the 16-bit fields; the producer validates them itself)
-          if (round_out > out_size - pos) err = kPageErrOverrun;
-          const uint32_t baddist = __ballot_sync(kFull, has_copy && (dist == 0 || dist > o_cpy));
-          if (baddist && !err) err = kPageErrDistance;
-        }
-        if (err) {
-          if (lane == 0) ctl->err = err;
-        } else if (rflags & 2u) {
-          // ---- slow round: hand a fully flushed page over to the producer
-          flush_bytes(sm, out, flushed, pos, lane);
-          flushed = pos;
-          await_slow = true;
-          slow_was_last = (rflags & 1u) != 0;
-          if (lane == 0) { ctl->pos = pos; ctl->slow = 2u; }
-        } else {
-          const uint32_t lq = incl_ins - ins;                // round-local index of this command's first literal
-          const int32_t ring_lo = ring_from > (int32_t)round_end - (int32_t)kRing ? ring_from : (int32_t)round_end - (int32_t)kRing;
-#ifdef BGX_STATS
-          {
-            const uint32_t mi = __reduce_max_sync(kFull, ins < kCoopLen ? ins : 0u);
-            const uint32_t ncp = __popc(__ballot_sync(kFull, cpy != 0));
-            const uint32_t far = __reduce_add_sync(kFull, (cpy && dist > 1500u) ? cpy : 0u);
-            const uint32_t ov = __popc(__ballot_sync(kFull, cpy != 0 && dist < cpy));
-            BGX_STAT(emu_stats().sum_max_ins += mi; emu_stats().ins_bytes += round_ins; emu_stats().copies += ncp;
-                     emu_stats().copy_bytes += round_out - round_ins; emu_stats().far_bytes += far; emu_stats().overlap_copies += ov);
-          }
+  if (warp_index() == 0) producer_warp(job, sm);
+  else consumer_warp(job, sm);
+  __syncthreads();
+  PageResult res;
+  res.status = sm->ctl.err;
+  res.is_delta = sm->ctl.is_delta;
+#ifdef BGX_EMULATED
+  if (!wemu::named_bars_idle()) { fprintf(stderr, "decode_page_cta: the slow-round barrier was left pending\n"); abort(); }
 #endif
-          // ---- inserts, flattened: lane t places literal t of the round (perfectly balanced, any length).
-          //      Commands with literals are compacted into tab[]; a per-chunk bit mask of their first
-          //      literal index turns "which command owns literal t" into one popc.
-          uint32_t* tab = sm->scratch;                       // [32] (o_ins - first literal index)
-          const saddr_t ring_a = saddr(sm->ring), litq_a = saddr(sm->litq), tab_a = saddr(sm->scratch);
-          {
-            const uint32_t has = __ballot_sync(kFull, ins != 0);
-            if (ins) tab[__popc(has & lt_mask)] = o_ins - lq;
-            __syncwarp();
-            const uint32_t icidx = lq >> 5;
-            const uint32_t icbit = ins ? (1u << (lq & 31u)) : 0u;
-            const uint32_t ilast = __popc(has) - 1u;
-            uint32_t before = 0;
-            for (uint32_t c = 0, c0 = 0; c0 < round_ins; ++c, c0 += 32) {
-              const uint32_t M = __reduce_or_sync(kFull, icidx == c ? icbit : 0u);
-              const uint32_t t = c0 + lane;
-              uint32_t ord = before + __popc(M & le_mask) - 1u;
-              before += __popc(M);
-              ord = ord < ilast ? ord : ilast;
-              const uint32_t base = lds_u32(tab_a + 4u * ord);
-              if (t < round_ins)   // (lanes past the round's last literal must not touch slots the producer is filling)
-                sts_u8(ring_a + ((base + t) & (kRing - 1)), lds_u8(litq_a + ((lit_head + t) & (kLitQ - 1))));
-            }
-          }
-          __syncwarp();
-          // ---- copies. Wavefront 1 (flattened, like the inserts): every copy whose source already is
-          //      final, i.e. lies below the destination of the first pending copy. Sources may be in
-          //      the ring or (far matches) in L1/L2.
-          const uint32_t src_hi = o_cpy - dist + (cpy < dist ? cpy : dist);  // one past the last distinct source byte
-          uint32_t pending = __ballot_sync(kFull, cpy != 0);
-          if (pending) {
-            const int first = __ffs((int)pending) - 1;
-            const uint32_t hwm = __shfl_sync(kFull, o_cpy, first);           // everything below is final
-            const bool ready1 = cpy != 0 && dist >= cpy && ((int)lane == first || src_hi <= hwm);
-            const uint32_t len1 = ready1 ? cpy : 0u;
-            const uint32_t E1 = warp_incl_scan(len1, lane);
-            const uint32_t T1 = __shfl_sync(kFull, E1, 31);
-            const uint32_t S1 = E1 - len1;
-            const uint32_t m1 = __ballot_sync(kFull, ready1);
-            uint2* tab2 = reinterpret_cast<uint2*>(sm->scratch + 32);        // [32] (dst - first flat index, distance)
-            if (ready1) tab2[__popc(m1 & lt_mask)] = make_uint2(o_cpy - S1, dist);
-            __syncwarp();
-            const uint32_t cidx = S1 >> 5;
-            const uint32_t cbit = ready1 ? (1u << (S1 & 31u)) : 0u;
-            const uint32_t last = __popc(m1) - 1u;
-            uint32_t before = 0;
-            const saddr_t tab2_a = tab_a + 128u;
-            // NU 32-byte chunks per trip; all loads of a trip are issued before its stores
-            auto trip = [&](auto nu_tag, uint32_t c, uint32_t c0) {
-              constexpr int NU = decltype(nu_tag)::value;
-              uint32_t M[NU];
-#pragma unroll
-              for (int u = 0; u < NU; ++u) M[u] = __reduce_or_sync(kFull, cidx == c + u ? cbit : 0u);
-              uint32_t d[NU];
-              uint32_t v[NU];
-#pragma unroll
-              for (int u = 0; u < NU; ++u) {
-                const uint32_t t = c0 + 32u * u + lane;
-                uint32_t ord = before + __popc(M[u] & le_mask) - 1u;
-                before += __popc(M[u]);
-                ord = ord < last ? ord : last;                               // lanes past the end read a valid entry
-                const uint2 q = lds_u32x2(tab2_a + 8u * ord);
-                d[u] = q.x + t;
-                const uint32_t sp = d[u] - q.y;
-                const bool ok = t < T1;
-                const bool near = (int32_t)sp >= ring_lo;
-                v[u] = 0;
-                if (ok && near) v[u] = lds_u8(ring_a + (sp & (kRing - 1)));
-                if (ok && !near) v[u] = ldg_u8(out + sp);
-                if (!ok) d[u] = 0xffffffffu;
-              }
-#pragma unroll
-              for (int u = 0; u < NU; ++u)
-                if (d[u] != 0xffffffffu) sts_u8(ring_a + (d[u] & (kRing - 1)), v[u]);
-            };
-            uint32_t c = 0, c0 = 0;
-            for (; c0 + 64u < T1; c += 4, c0 += 128) trip(std::integral_constant<int, 4>{}, c, c0);
-            if (c0 < T1) {
-              if (T1 - c0 > 32u) trip(std::integral_constant<int, 2>{}, c, c0);
-              else trip(std::integral_constant<int, 1>{}, c, c0);
-            }
-            __syncwarp();
-            pending &= ~m1;
-          }
-          //      Remaining copies (dependent on this round's copies, or overlapping themselves): in command
-          //      order, each by the whole warp (lane j moves byte j; almost always a single step). In-order
-          //      execution satisfies every dependency; an overlapping copy (dist < len) repeats its
-          //      `dist`-byte pattern exactly as the byte-serial reference loop does (PageDecoder.cpp:222-232).
-          while (pending) {
-            const int k = __ffs((int)pending) - 1;
-            pending &= pending - 1;
-            const uint32_t n_k = __shfl_sync(kFull, cpy, k);
-            const uint32_t o_k = __shfl_sync(kFull, o_cpy, k);
-            const uint32_t d_k = __shfl_sync(kFull, dist, k);
-            BGX_STAT(emu_stats().wavefronts++; emu_stats().sum_max_cpy += n_k);
-            for (uint32_t j = lane; j < n_k; j += 32) {
-              const uint32_t m = j < d_k ? j : j % d_k;
-              const uint32_t sp = o_k - d_k + m;
-              const uint32_t v = ((int32_t)sp >= ring_lo) ? lds_u8(ring_a + (sp & (kRing - 1))) : ldg_u8(out + sp);
-              sts_u8(ring_a + ((o_k + j) & (kRing - 1)), v);
-            }
-            __syncwarp();
-          }
-          pos = round_end;
-          lit_head += round_ins;
-          // ---- write-combined flush of complete 512-byte chunks
-          if (pos - flushed >= kFlushChunk) {
-            if (out_aligned) {
-              if (flushed & 15u) {   // after a cooperative (direct) episode the flush point may be unaligned
-                const uint32_t to = (flushed + 15u) & ~15u;
-                flush_bytes(sm, out, flushed, to, lane);
-                flushed = to;
-              }
-              while (pos - flushed >= kFlushChunk) {
-                const uint32_t q = flushed + 16u * lane;
-                *reinterpret_cast<uint4*>(out + q) = *reinterpret_cast<const uint4*>(&sm->ring[q & (kRing - 1)]);
-                flushed += kFlushChunk;
-              }
-            } else {
-              const uint32_t to = flushed + ((pos - flushed) / kFlushChunk) * kFlushChunk;
-              flush_bytes(sm, out, flushed, to, lane);
-              flushed = to;
-            }
-            __syncwarp();
-          }
-          if (rflags & 1u) {
-            // ---- last round: whatever is still only in the ring, then zero-fill (the reference memsets the page first)
-            flush_bytes(sm, out, flushed, pos, lane);
-            for (uint32_t q = pos + lane; q < out_size; q += 32) out[q] = 0;
-            if (lane == 0) ctl->finished = 1u;
-          }
-          if (lane == 0) ctl->consumed = C + 1u;
-        }
-      }
-    }
-    __syncthreads();
-  }
-  res.status = ctl->err;
-  res.is_delta = ctl->is_delta;
   __syncthreads();     // everybody has read the result before the page arena is reused
   return res;
 }

@@ -53,6 +53,7 @@ struct Block {
   int cur = 0;
   Rendezvous warp[kMaxWarps];
   Rendezvous block;
+  struct NamedBar { int arrived = 0; uint64_t gen = 0; } nbar[16];   // bar.sync / bar.arrive with an id
   uint64_t collectives = 0;
   std::function<void()> body;
 };
@@ -100,6 +101,54 @@ inline void rendezvous(Rendezvous& r, int count, int me, int op, uint64_t v, uin
 inline void rendezvous(int op, uint64_t v, uint32_t aux, const uint64_t** vals, const uint32_t** auxs) {
   Block* b = B();
   rendezvous(b->warp[b->cur >> 5], 32, b->cur & 31, op, v, aux, vals, auxs);
+}
+
+// Named CTA barriers (PTX bar.sync / bar.arrive id, count): a phase completes when `count` threads have
+// arrived; bar.arrive does not wait, bar.sync waits for the phase it arrived in to complete.
+inline void named_bar_arrive(int id, int count) {
+  Block* b = B();
+  Block::NamedBar& nb = b->nbar[id];
+  if (++nb.arrived == count) {
+    nb.arrived = 0;
+    nb.gen++;
+    b->collectives++;
+  } else if (nb.arrived > count) {
+    fprintf(stderr, "warp_emul: named barrier %d over-subscribed\n", id);
+    abort();
+  }
+}
+inline void named_bar_sync(int id, int count) {
+  Block* b = B();
+  Block::NamedBar& nb = b->nbar[id];
+  const uint64_t g = nb.gen;
+  if (++nb.arrived == count) {
+    nb.arrived = 0;
+    nb.gen++;
+    b->collectives++;
+  } else {
+    while (nb.gen == g) yield_to_sched();
+  }
+}
+// mbarrier objects (8 bytes in shared memory): low word = pending arrivals, high word = count << 1 | phase.
+inline void mbar_init(uint64_t* m, uint32_t count) { *m = ((uint64_t)((count << 1) | 0u) << 32) | count; }
+inline void mbar_arrive(uint64_t* m) {
+  uint32_t pending = (uint32_t)*m, hi = (uint32_t)(*m >> 32);
+  if (pending == 0 || (hi >> 1) == 0) { fprintf(stderr, "warp_emul: arrive on an uninitialised mbarrier\n"); abort(); }
+  if (--pending == 0) {
+    hi ^= 1u;             // next phase
+    pending = hi >> 1;
+    B()->collectives++;
+  }
+  *m = ((uint64_t)hi << 32) | pending;
+}
+inline void mbar_wait(uint64_t* m, uint32_t parity) {   // returns once the phase with this parity has completed
+  while ((((uint32_t)(*(volatile uint64_t*)m >> 32)) & 1u) == (parity & 1u)) yield_to_sched();
+}
+inline bool named_bars_idle() {
+  Block* b = B();
+  for (int i = 0; i < 16; ++i)
+    if (b->nbar[i].arrived) return false;
+  return true;
 }
 
 inline void check_mask(unsigned mask) {
