@@ -125,6 +125,7 @@ BGX_DEV void sts_u8(saddr_t a, uint32_t v) { *reinterpret_cast<uint8_t*>(a) = (u
 BGX_DEV uint32_t lds_u32(saddr_t a) { return *reinterpret_cast<const uint32_t*>(a); }
 BGX_DEV uint2 lds_u32x2(saddr_t a) { return *reinterpret_cast<const uint2*>(a); }
 BGX_DEV uint32_t ldg_u8(const uint8_t* p) { return *p; }
+BGX_DEV uint32_t ldg_u32(const uint32_t* p) { return *p; }
 #else
 typedef uint32_t saddr_t;
 BGX_DEV saddr_t saddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -133,6 +134,7 @@ BGX_DEV void sts_u8(saddr_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1
 BGX_DEV uint32_t lds_u32(saddr_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 BGX_DEV uint2 lds_u32x2(saddr_t a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
 BGX_DEV uint32_t ldg_u8(const uint8_t* p) { uint32_t v; asm volatile("ld.global.u8 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
+BGX_DEV uint32_t ldg_u32(const uint32_t* p) { uint32_t v; asm volatile("ld.global.u32 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
 #endif
 
 // ---------------------------------------------------------------------------------------------
@@ -926,6 +928,7 @@ BGX_DEV void consumer_warp(const PageJob& job, WarpSmem* sm) {
   uint32_t lit_head = 0;       // page-global literal index of the next literal to place
   bool failed = false;         // a round was rejected: only keep the hand-over going until the producer stops
   const bool out_aligned = (reinterpret_cast<uintptr_t>(out) & 15u) == 0;
+  const bool out_al4 = (reinterpret_cast<uintptr_t>(out) & 3u) == 0;
   const saddr_t full_a = saddr(sm->mbar), empty_a = full_a + 8u * kQ;
 
   for (uint32_t r = 0;; ++r) {
@@ -947,7 +950,12 @@ BGX_DEV void consumer_warp(const PageJob& job, WarpSmem* sm) {
       bar_sync_slow();
       pos = ctl->pos;
       flushed = pos;
-      ring_from = (int32_t)pos;
+      {   // the ring restarts 4 bytes below the hand-over point, so that flushed >= ring_lo + 4 keeps holding
+        const uint32_t back = pos < 4u ? pos : 4u;
+        if (lane < back) sm->ring[(pos - back + lane) & (kRing - 1)] = out[pos - back + lane];
+        ring_from = (int32_t)(pos - back);
+        __syncwarp();
+      }
       lit_head = ctl->lit_head;
       warp_arrive(empty_a + 8u * q, lane);
       if (rflags & kFlagLast) {
@@ -1022,61 +1030,65 @@ BGX_DEV void consumer_warp(const PageJob& job, WarpSmem* sm) {
       }
     }
     warp_arrive(empty_a + 8u * q, lane);   // the RoundBuf and this round's literals are no longer needed
-    // ---- copies. Wavefront 1 (flattened, like the inserts): every copy whose source already is
-    //      final, i.e. lies below the destination of the first pending copy. Sources may be in
-    //      the ring or (far matches) in L1/L2.
-    const uint32_t src_hi = o_cpy - dist + (cpy < dist ? cpy : dist);  // one past the last distinct source byte
+    // ---- copies. Wavefront 1: every copy whose source already is final, i.e. lies below the destination of
+    //      the first pending copy, flattened over 4-byte PIECES: lane t moves piece t of the wavefront
+    //      (perfectly balanced, any length mix). Ready copies are compacted into tab2[]; a per-chunk bit
+    //      mask of their first piece index turns "which copy owns piece t" into one popc. A piece is
+    //      fetched as two aligned words + a funnel shift, from the ring (near) or from L1/L2 (far matches;
+    //      everything below `flushed` is in global memory, and flushed >= ring_lo + 4 always holds).
     uint32_t pending = __ballot_sync(kFull, cpy != 0);
     if (pending) {
       const int first = __ffs((int)pending) - 1;
       const uint32_t hwm = __shfl_sync(kFull, o_cpy, first);           // everything below is final
-      const bool ready1 = cpy != 0 && dist >= cpy && ((int)lane == first || src_hi <= hwm);
-      const uint32_t len1 = ready1 ? cpy : 0u;
-      const uint32_t E1 = warp_incl_scan(len1, lane);
+      const bool ready1 = cpy != 0 && dist >= cpy && ((int)lane == first || o_cpy - dist + cpy <= hwm);
+      const uint32_t np1 = ready1 ? (cpy + 3u) >> 2 : 0u;
+      const uint32_t E1 = warp_incl_scan(np1, lane);
       const uint32_t T1 = __shfl_sync(kFull, E1, 31);
-      const uint32_t S1 = E1 - len1;
+      const uint32_t S1 = E1 - np1;
       const uint32_t m1 = __ballot_sync(kFull, ready1);
-      uint2* tab2 = reinterpret_cast<uint2*>(sm->scratch + 32);        // [32] (dst - first flat index, distance)
-      if (ready1) tab2[__popc(m1 & lt_mask)] = make_uint2(o_cpy - S1, dist);
+      // entry: (dst - 4 * first piece index, distance | (end - that) << 17); page <= 128 KiB, round <= kRoundMax
+      uint2* tab2 = reinterpret_cast<uint2*>(sm->scratch + 32);        // [32]
+      if (ready1) tab2[__popc(m1 & lt_mask)] = make_uint2(o_cpy - 4u * S1, dist | ((4u * S1 + cpy) << 17));
       __syncwarp();
       const uint32_t cidx = S1 >> 5;
       const uint32_t cbit = ready1 ? (1u << (S1 & 31u)) : 0u;
       const uint32_t last = __popc(m1) - 1u;
-      uint32_t before = 0;
       const saddr_t tab2_a = tab_a + 128u;
-      // NU 32-byte chunks per trip; all loads of a trip are issued before its stores
-      auto trip = [&](auto nu_tag, uint32_t c, uint32_t c0) {
-        constexpr int NU = decltype(nu_tag)::value;
-        uint32_t M[NU];
-#pragma unroll
-        for (int u = 0; u < NU; ++u) M[u] = __reduce_or_sync(kFull, cidx == c + u ? cbit : 0u);
-        uint32_t d[NU];
-        uint32_t v[NU];
-#pragma unroll
-        for (int u = 0; u < NU; ++u) {
-          const uint32_t t = c0 + 32u * u + lane;
-          uint32_t ord = before + __popc(M[u] & le_mask) - 1u;
-          before += __popc(M[u]);
-          ord = ord < last ? ord : last;                               // lanes past the end read a valid entry
-          const uint2 q = lds_u32x2(tab2_a + 8u * ord);
-          d[u] = q.x + t;
-          const uint32_t sp = d[u] - q.y;
-          const bool ok = t < T1;
-          const bool near = (int32_t)sp >= ring_lo;
-          v[u] = 0;
-          if (ok && near) v[u] = lds_u8(ring_a + (sp & (kRing - 1)));
-          if (ok && !near) v[u] = ldg_u8(out + sp);
-          if (!ok) d[u] = 0xffffffffu;
+      uint32_t before = 0;
+#pragma unroll 1
+      for (uint32_t c = 0, t = lane; 32u * c < T1; ++c, t += 32u) {
+        const uint32_t M = __reduce_or_sync(kFull, cidx == c ? cbit : 0u);
+        uint32_t ord = before + __popc(M & le_mask) - 1u;
+        before += __popc(M);
+        ord = ord < last ? ord : last;                                 // lanes past the end read a valid entry
+        const uint2 e = lds_u32x2(tab2_a + 8u * ord);
+        const uint32_t d = e.x + 4u * t;                               // destination of this piece
+        const uint32_t sp = d - (e.y & 0x1ffffu);                      // its source
+        int32_t rem = (int32_t)((e.y >> 17) - 4u * t);                 // bytes of the copy from this piece on
+        if (t >= T1) rem = 0;
+        uint32_t lo = 0, hi = 0;
+        if (rem > 0) {
+          if ((int32_t)sp >= ring_lo) {
+            const uint32_t a = sp & (kRing - 4u);
+            lo = lds_u32(ring_a + a);
+            hi = lds_u32(ring_a + ((a + 4u) & (kRing - 1)));
+          } else if (out_al4) {
+            const uint32_t* g = reinterpret_cast<const uint32_t*>(out + (sp & ~3u));
+            lo = ldg_u32(g);
+            if ((sp & 3u) + (uint32_t)rem > 4u) hi = ldg_u32(g + 1);   // only when it holds a byte of the source
+          } else {
+            lo = ldg_u8(out + sp);
+            if (rem > 1) lo |= ldg_u8(out + sp + 1) << 8;
+            if (rem > 2) lo |= ldg_u8(out + sp + 2) << 16;
+            if (rem > 3) lo |= ldg_u8(out + sp + 3) << 24;
+          }
         }
-#pragma unroll
-        for (int u = 0; u < NU; ++u)
-          if (d[u] != 0xffffffffu) sts_u8(ring_a + (d[u] & (kRing - 1)), v[u]);
-      };
-      uint32_t c = 0, c0 = 0;
-      for (; c0 + 64u < T1; c += 4, c0 += 128) trip(std::integral_constant<int, 4>{}, c, c0);
-      if (c0 < T1) {
-        if (T1 - c0 > 32u) trip(std::integral_constant<int, 2>{}, c, c0);
-        else trip(std::integral_constant<int, 1>{}, c, c0);
+        const uint32_t sh = ((int32_t)sp >= ring_lo || out_al4) ? (sp & 3u) * 8u : 0u;
+        const uint32_t v = __funnelshift_r(lo, hi, sh);
+        if (rem > 0) sts_u8(ring_a + (d & (kRing - 1)), v);
+        if (rem > 1) sts_u8(ring_a + ((d + 1u) & (kRing - 1)), v >> 8);
+        if (rem > 2) sts_u8(ring_a + ((d + 2u) & (kRing - 1)), v >> 16);
+        if (rem > 3) sts_u8(ring_a + ((d + 3u) & (kRing - 1)), v >> 24);
       }
       __syncwarp();
       pending &= ~m1;
@@ -1085,6 +1097,7 @@ BGX_DEV void consumer_warp(const PageJob& job, WarpSmem* sm) {
     //      order, each by the whole warp (lane j moves byte j; almost always a single step). In-order
     //      execution satisfies every dependency; an overlapping copy (dist < len) repeats its
     //      `dist`-byte pattern exactly as the byte-serial reference loop does (PageDecoder.cpp:222-232).
+#pragma unroll 1
     while (pending) {
       const int k = __ffs((int)pending) - 1;
       pending &= pending - 1;
@@ -1092,11 +1105,20 @@ BGX_DEV void consumer_warp(const PageJob& job, WarpSmem* sm) {
       const uint32_t o_k = __shfl_sync(kFull, o_cpy, k);
       const uint32_t d_k = __shfl_sync(kFull, dist, k);
       BGX_STAT(emu_stats().wavefronts++; emu_stats().sum_max_cpy += n_k);
-      for (uint32_t j = lane; j < n_k; j += 32) {
-        const uint32_t m = j < d_k ? j : j % d_k;
-        const uint32_t sp = o_k - d_k + m;
-        const uint32_t v = ((int32_t)sp >= ring_lo) ? lds_u8(ring_a + (sp & (kRing - 1))) : ldg_u8(out + sp);
-        sts_u8(ring_a + ((o_k + j) & (kRing - 1)), v);
+      if (n_k <= 32u && d_k >= n_k) {                                  // the usual case: one step, no overlap
+        if (lane < n_k) {
+          const uint32_t sp = o_k - d_k + lane;
+          const uint32_t v = ((int32_t)sp >= ring_lo) ? lds_u8(ring_a + (sp & (kRing - 1))) : ldg_u8(out + sp);
+          sts_u8(ring_a + ((o_k + lane) & (kRing - 1)), v);
+        }
+      } else {
+#pragma unroll 1
+        for (uint32_t j = lane; j < n_k; j += 32) {
+          const uint32_t m = j < d_k ? j : j % d_k;
+          const uint32_t sp = o_k - d_k + m;
+          const uint32_t v = ((int32_t)sp >= ring_lo) ? lds_u8(ring_a + (sp & (kRing - 1))) : ldg_u8(out + sp);
+          sts_u8(ring_a + ((o_k + j) & (kRing - 1)), v);
+        }
       }
       __syncwarp();
     }

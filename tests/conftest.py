@@ -104,14 +104,16 @@ class Emulator:
         self.lib = ctypes.CDLL(so)
         self.lib.emul_decode_stream.restype = ctypes.c_int
 
-    def decode(self, stream: np.ndarray, expect_rc: int = 0):
+    def decode(self, stream: np.ndarray, expect_rc: int = 0, dst_offset: int = 0):
         s = np.ascontiguousarray(stream, dtype=np.uint8)
         n = (int(s[2]) | (int(s[3]) << 8))
         w1 = int(s[4]) | (int(s[5]) << 8) | (int(s[6]) << 16) | (int(s[7]) << 24)
         ps = 32768 << (w1 & 3)
         last = (w1 >> 2) & 0x3FFFF
         size = n * ps - ((ps - last) if last else 0)
-        out = np.full(size + 64, 0xEE, dtype=np.uint8)
+        base = np.full(size + 64 + 32, 0xEE, dtype=np.uint8)
+        skew = (-base.ctypes.data) % 16 + dst_offset          # output starts `dst_offset` bytes past a 16-byte boundary
+        out = base[skew: skew + size + 64]
         st = (ctypes.c_uint32 * max(n, 1))()
         fl = (ctypes.c_uint32 * max(n, 1))()
         coll = ctypes.c_uint64(0)

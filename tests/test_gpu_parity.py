@@ -131,6 +131,28 @@ def test_device_resident_plan_with_page_ranges(sdk, dec):
     assert np.array_equal(np.concatenate(shards), data)
 
 
+def test_device_output_at_any_alignment(sdk, oracle, dec):
+    """the output pointer of a device-resident decode may have any alignment (byte-granular flush and
+    far-match paths of the page kernel; raw pages fall back to narrower copies)"""
+    import torch
+    from brotli_g_sdk_b200 import datagen
+    data = np.concatenate([datagen.text_like(200000, seed=41), datagen.random_bytes(70000, seed=42),
+                           datagen.structured_binary(100000, seed=43), np.zeros(4000, np.uint8)])
+    s = sdk.Encode(data)
+    want = oracle.decode(s)
+    t_in = torch.zeros(len(s) + 64, dtype=torch.uint8, device="cuda")
+    t_in[: len(s)] = torch.from_numpy(s).cuda()
+    for off in (1, 2, 3, 4, 8):
+        t_out = torch.full((len(data) + 64,), 0xEE, dtype=torch.uint8, device="cuda")
+        plan = dec.plan([dict(d_src=t_in.data_ptr(), src_size=len(s), src_capacity=len(s) + 64, d_dst=t_out.data_ptr() + off,
+                              dst_capacity=len(data), header=bytes(s[:16]))])
+        plan.launch(torch.cuda.current_stream().cuda_stream)
+        assert plan.finish() == 0
+        got = t_out.cpu().numpy()
+        assert np.array_equal(got[off: off + len(data)], want), f"offset {off}"
+        assert (got[:off] == 0xEE).all() and (got[off + len(data):] == 0xEE).all(), f"offset {off}: wrote outside the buffer"
+
+
 def test_full_size_random_buffer_checksum_of_checksums(sdk, dec):
     """BASELINE config 2 shape (64 MiB streams of raw pages), 1 GiB here: per-page CRCs of the decoded
     buffer equal those of the source (checked on the device side via torch, no oracle at this size)."""
