@@ -7,7 +7,8 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-CUDA_LIB_PATH = os.path.join(HERE, "libbrotlig_b200.so")
+# BGX_CUDA_LIB lets kernel experiments load an alternative build of the same library (scripts/variants.sh)
+CUDA_LIB_PATH = os.environ.get("BGX_CUDA_LIB") or os.path.join(HERE, "libbrotlig_b200.so")
 ENC_LIB_PATH = os.path.join(HERE, "libbrotlig_b200_enc.so")
 
 _cuda = None

@@ -44,7 +44,10 @@ struct QueueCtl {
 
 constexpr int kPageThreads = 64;   // two warps per page: producer (entropy decode) + consumer (LZ77 assembly)
 
-__global__ void __launch_bounds__(kPageThreads, 16) bgx_decode_pages_kernel(const StreamDev* __restrict__ streams, uint32_t nstreams,
+#ifndef BGX_CTAS_PER_SM
+#define BGX_CTAS_PER_SM 16
+#endif
+__global__ void __launch_bounds__(kPageThreads, BGX_CTAS_PER_SM) bgx_decode_pages_kernel(const StreamDev* __restrict__ streams, uint32_t nstreams,
                                                                         uint32_t q_begin, uint32_t q_end, QueueCtl* ctl,
                                                                         uint32_t* __restrict__ page_status) {
   __shared__ bgxk::WarpSmem sm;

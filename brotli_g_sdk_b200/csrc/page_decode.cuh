@@ -41,6 +41,9 @@
 #define BGX_DEV_NOINLINE inline
 #endif
 
+#ifndef BGX_WAIT_HINT_NS
+#define BGX_WAIT_HINT_NS 20000u
+#endif
 #ifndef BGX_RAW_PATH
 #define BGX_RAW_PATH 1
 #endif
@@ -61,7 +64,10 @@ constexpr int kCmdLutBits = 9;
 constexpr int kLitLutBits = 10;
 constexpr int kDistLutBits = 9;
 constexpr uint32_t kLitQ = 512;       // literal ring bytes (power of two): two rounds' literals (producer runs one ahead)
-constexpr uint32_t kRing = 2048;      // output ring bytes (power of two, >= kFlushChunk + kRoundMax)
+#ifndef BGX_RING
+#define BGX_RING 2048
+#endif
+constexpr uint32_t kRing = BGX_RING;      // output ring bytes (power of two, >= kFlushChunk + kRoundMax)
 constexpr uint32_t kRoundMax = 1024;  // largest round (bytes produced) the ring path accepts
 constexpr uint32_t kFlushChunk = 512; // 32 lanes x 16 B
 constexpr uint32_t kCoopLen = 32;     // inserts/copies at least this long are done by the whole warp
@@ -81,7 +87,10 @@ struct HuffAux {
   uint16_t base[16];    // base[L]  = offset_in_sorted[L] - first_code[L]   (mod 2^16)
 };
 
-constexpr uint32_t kQ = 4;   // rounds in flight between the producer and the consumer warp (power of two)
+#ifndef BGX_Q
+#define BGX_Q 4
+#endif
+constexpr uint32_t kQ = BGX_Q;   // rounds in flight between the producer and the consumer warp (power of two)
 struct RoundBuf {            // one round of <= 32 commands, producer -> consumer (only rounds of <= kRoundMax bytes;
   uint32_t dx[32];           //   resolved match distance              long-run rounds stay in the producer's registers)
   uint32_t pk[32];           //   inclusive prefix sums over the commands: bytes produced | literals consumed << 16
@@ -209,6 +218,24 @@ BGX_DEV void br_topup(const BitRd& r, PageIn& in) {
     stage_issue(in, in.issued);
     ++in.issued;
   }
+}
+// Hot-path variant: at most one new chunk can be due when no more than 4 words were fetched since the last top-up.
+BGX_DEV void br_topup1(const BitRd& r, PageIn& in) {
+#ifdef BGX_TOPUP_WHILE
+  br_topup(r, in);
+#else
+  if (in.issued < (r.k4 >> 4) + 4u) {
+    cp_async_wait<0>();
+#ifdef BGX_EMULATED
+    in.landed = in.issued;
+#endif
+    stage_issue(in, in.issued);
+    ++in.issued;
+  }
+#ifdef BGX_EMULATED
+  if (in.issued < (r.k4 >> 4) + 4u) { fprintf(stderr, "bit reader: more than one chunk due at a hot top-up\n"); abort(); }
+#endif
+#endif
 }
 BGX_DEV uint32_t stage_word(const PageIn& in, uint32_t k4) {
 #ifdef BGX_EMULATED
@@ -524,7 +551,7 @@ BGX_DEV void decode_literals(WarpSmem* sm, BitRd& rd, PageIn& in, uint32_t tail,
   // with a pair whose second half is neither stored nor consumed.
 #pragma unroll 1
   for (uint32_t j = 0; j < cnt; j += 2) {
-    br_topup(rd, in);
+    br_topup1(rd, in);
     const uint32_t pk = br_peek(rd);
     uint32_t len1, len2;
     const uint32_t s1 = huff_decode<kLitLutBits>(sm->lut_lit, sm->aux[2], sm->sorted_lit, bgx::kNumLitSymbols, pk, len1);
@@ -592,10 +619,10 @@ BGX_DEV void mbar_wait(saddr_t a, uint32_t parity) {
   asm volatile(
       "{\n\t.reg .pred p;\n"
       "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"   // suspends up to the time hint: no busy spin
       "@p bra DONE_%=;\n\t"
       "bra WAIT_%=;\n"
-      "DONE_%=:\n\t}" ::"r"(a), "r"(parity) : "memory");
+      "DONE_%=:\n\t}" ::"r"(a), "r"(parity), "r"(BGX_WAIT_HINT_NS) : "memory");
 #endif
 }
 // the whole warp signals: its earlier shared-memory accesses are ordered before the elected lane's arrive
@@ -688,7 +715,7 @@ BGX_DEV void producer_warp(const PageJob& job, WarpSmem* sm) {
       break;
     }
     RoundBuf* rb = &sm->rb[q];
-    br_topup(rd, in);
+    br_topup1(rd, in);
     // ---- one command per lane, speculatively (lanes after the sentinel roll back)
     BitRd r = rd;
     uint32_t len;
@@ -1055,18 +1082,19 @@ BGX_DEV void consumer_warp(const PageJob& job, WarpSmem* sm) {
       const uint32_t last = __popc(m1) - 1u;
       const saddr_t tab2_a = tab_a + 128u;
       uint32_t before = 0;
-#pragma unroll 1
-      for (uint32_t c = 0, t = lane; 32u * c < T1; ++c, t += 32u) {
+      // fetch: owner look-up + the two source words of piece t; place: the (up to) four byte stores
+      auto fetch = [&](uint32_t c, uint32_t t, uint32_t& d, int32_t& rem, uint32_t& lo, uint32_t& hi, uint32_t& sh) {
         const uint32_t M = __reduce_or_sync(kFull, cidx == c ? cbit : 0u);
         uint32_t ord = before + __popc(M & le_mask) - 1u;
         before += __popc(M);
         ord = ord < last ? ord : last;                                 // lanes past the end read a valid entry
         const uint2 e = lds_u32x2(tab2_a + 8u * ord);
-        const uint32_t d = e.x + 4u * t;                               // destination of this piece
+        d = e.x + 4u * t;                                              // destination of this piece
         const uint32_t sp = d - (e.y & 0x1ffffu);                      // its source
-        int32_t rem = (int32_t)((e.y >> 17) - 4u * t);                 // bytes of the copy from this piece on
+        rem = (int32_t)((e.y >> 17) - 4u * t);                         // bytes of the copy from this piece on
         if (t >= T1) rem = 0;
-        uint32_t lo = 0, hi = 0;
+        lo = 0; hi = 0;
+        sh = (sp & 3u) * 8u;
         if (rem > 0) {
           if ((int32_t)sp >= ring_lo) {
             const uint32_t a = sp & (kRing - 4u);
@@ -1081,14 +1109,23 @@ BGX_DEV void consumer_warp(const PageJob& job, WarpSmem* sm) {
             if (rem > 1) lo |= ldg_u8(out + sp + 1) << 8;
             if (rem > 2) lo |= ldg_u8(out + sp + 2) << 16;
             if (rem > 3) lo |= ldg_u8(out + sp + 3) << 24;
+            sh = 0;
           }
         }
-        const uint32_t sh = ((int32_t)sp >= ring_lo || out_al4) ? (sp & 3u) * 8u : 0u;
+      };
+      auto place = [&](uint32_t d, int32_t rem, uint32_t lo, uint32_t hi, uint32_t sh) {
         const uint32_t v = __funnelshift_r(lo, hi, sh);
         if (rem > 0) sts_u8(ring_a + (d & (kRing - 1)), v);
         if (rem > 1) sts_u8(ring_a + ((d + 1u) & (kRing - 1)), v >> 8);
         if (rem > 2) sts_u8(ring_a + ((d + 2u) & (kRing - 1)), v >> 16);
         if (rem > 3) sts_u8(ring_a + ((d + 3u) & (kRing - 1)), v >> 24);
+      };
+#pragma unroll 1
+      for (uint32_t c = 0, t = lane; 32u * c < T1; ++c, t += 32u) {
+        uint32_t d, lo, hi, sh;
+        int32_t rem;
+        fetch(c, t, d, rem, lo, hi, sh);
+        place(d, rem, lo, hi, sh);
       }
       __syncwarp();
       pending &= ~m1;

@@ -94,13 +94,14 @@ class Emulator:
 
     def __init__(self):
         d = os.path.join(ROOT, "tests", "emul")
-        so = os.path.join(d, "libbgx_emul.so")
+        extra = os.environ.get("BGX_EMUL_FLAGS", "").split()     # e.g. -DBGX_PIECE_PREFETCH: emulate a kernel variant
+        so = os.path.join(d, "libbgx_emul%s.so" % ("_" + "".join(c for c in "".join(extra) if c.isalnum()) if extra else ""))
         deps = [os.path.join(d, "emul_decode.cpp"), os.path.join(d, "warp_emul.h"),
                 os.path.join(ROOT, "brotli_g_sdk_b200", "csrc", "page_decode.cuh"),
                 os.path.join(ROOT, "brotli_g_sdk_b200", "csrc", "bgx_format.h"),
                 os.path.join(ROOT, "brotli_g_sdk_b200", "csrc", "host_plan.h")]
         if not os.path.exists(so) or any(os.path.getmtime(x) > os.path.getmtime(so) for x in deps):
-            _run(["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-w", "-I" + d, deps[0], "-o", so])
+            _run(["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-w", "-I" + d] + extra + [deps[0], "-o", so])
         self.lib = ctypes.CDLL(so)
         self.lib.emul_decode_stream.restype = ctypes.c_int
 
