@@ -10,6 +10,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -259,6 +260,10 @@ int bgx_create(bgx_context** out, int device) {
     return bgx::kErrGeneric;
   }
   ctx->blocks_per_sm = per_sm;
+  if (const char* cap = getenv("BGX_CTAS_CAP")) {   // kernel experiments: fewer resident pages per SM
+    const int c = atoi(cap);
+    if (c >= 1 && c < per_sm) ctx->blocks_per_sm = c;
+  }
   *out = ctx;
   return bgx::kOk;
 }

@@ -41,8 +41,8 @@
 #define BGX_DEV_NOINLINE inline
 #endif
 
-#ifndef BGX_WAIT_HINT_NS
-#define BGX_WAIT_HINT_NS 20000u
+#ifndef BGX_WAIT_SLEEP_NS
+#define BGX_WAIT_SLEEP_NS 100
 #endif
 #ifndef BGX_RAW_PATH
 #define BGX_RAW_PATH 1
@@ -61,7 +61,10 @@ inline EmuStats& emu_stats() { static EmuStats s; return s; }
 
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kCmdLutBits = 9;
-constexpr int kLitLutBits = 10;
+#ifndef BGX_LITBITS
+#define BGX_LITBITS 10
+#endif
+constexpr int kLitLutBits = BGX_LITBITS;
 constexpr int kDistLutBits = 9;
 constexpr uint32_t kLitQ = 512;       // literal ring bytes (power of two): two rounds' literals (producer runs one ahead)
 #ifndef BGX_RING
@@ -616,13 +619,23 @@ BGX_DEV void mbar_wait(saddr_t a, uint32_t parity) {
 #ifdef BGX_EMULATED
   wemu::mbar_wait(reinterpret_cast<uint64_t*>(a), parity);
 #else
+  // try_wait suspends the warp for a short, hardware-defined time; a warp that still finds the phase open
+  // backs off with nanosleep instead of spinning (the waiting warp is the one that is ahead: its wake-up
+  // latency hides behind the rounds already queued), so waiting costs next to no issue slots.
+  uint32_t done;
   asm volatile(
-      "{\n\t.reg .pred p;\n"
-      "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"   // suspends up to the time hint: no busy spin
-      "@p bra DONE_%=;\n\t"
-      "bra WAIT_%=;\n"
-      "DONE_%=:\n\t}" ::"r"(a), "r"(parity), "r"(BGX_WAIT_HINT_NS) : "memory");
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(a), "r"(parity) : "memory");
+  while (!done) {
+#if BGX_WAIT_SLEEP_NS > 0
+    __nanosleep(BGX_WAIT_SLEEP_NS);
+#endif
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(a), "r"(parity) : "memory");
+  }
 #endif
 }
 // the whole warp signals: its earlier shared-memory accesses are ordered before the elected lane's arrive
