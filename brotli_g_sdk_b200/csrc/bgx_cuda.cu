@@ -54,6 +54,7 @@ __global__ void __launch_bounds__(kPageThreads, BGX_CTAS_PER_SM) bgx_decode_page
   __shared__ bgxk::WarpSmem sm;
   __shared__ uint32_t q_shared;
   const uint32_t tid = threadIdx.x;
+  uint32_t cur_stream = 0;   // owner of the last page this CTA decoded (streams are in queue order)
   if (tid == 0) q_shared = atomicAdd(&ctl->next_page, 1u);
   for (;;) {
     __syncthreads();
@@ -61,19 +62,35 @@ __global__ void __launch_bounds__(kPageThreads, BGX_CTAS_PER_SM) bgx_decode_page
     if (q >= q_end) break;
     uint32_t q_next = 0;
     if (tid == 0) q_next = atomicAdd(&ctl->next_page, 1u);   // claim the next page now: the atomic's latency hides behind this page
-    // stream owning queue slot q: last stream with first_q <= q
-    uint32_t lo = 0, hi = nstreams;
-    while (hi - lo > 1) {
-      const uint32_t mid = (lo + hi) >> 1;
-      if (streams[mid].first_q <= q) lo = mid; else hi = mid;
+    // stream owning queue slot q: last stream with first_q <= q. A CTA claims increasing slots, so the owner is
+    // almost always the previous page's stream or its successor: one load decides, the search only runs beyond.
+    uint32_t lo = cur_stream;
+    if (lo + 1 < nstreams && streams[lo + 1].first_q <= q) {
+      ++lo;
+      uint32_t hi = nstreams;
+      while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (streams[mid].first_q <= q) lo = mid; else hi = mid;
+      }
     }
+    cur_stream = lo;
     const StreamDev& s = streams[lo];
     const uint32_t page = s.page_begin + (q - s.first_q);
     StreamInfo si;
     si.num_pages = s.num_pages;
     si.page_size = s.page_size;
     si.last_page_size = s.last_page_size;
-    const bgx::PageExtent e = bgx::page_extent(si, s.table, page);
+    // page table entries as aligned 32-bit loads (the stream is 16-byte aligned, its headers are 8 or 16 bytes);
+    // same arithmetic as bgx::page_extent (host_plan.h)
+    bgx::PageExtent e;
+    {
+      const uint32_t* tbl = reinterpret_cast<const uint32_t*>(s.table);
+      const uint32_t t_next = tbl[page + 1 < si.num_pages ? page + 1 : 0];   // entry 0 holds the size of the last page
+      e.in_off = page ? tbl[page] : 0u;
+      e.in_size = (page + 1 < si.num_pages) ? t_next - e.in_off : t_next;
+      e.out_off = page * si.page_size;
+      e.out_size = (page + 1 == si.num_pages && si.last_page_size) ? si.last_page_size : si.page_size;
+    }
     const uint8_t* in = s.pages + e.in_off;
     uint8_t* out = s.dst + (size_t)(page - s.page_begin) * s.page_size;
     uint32_t status = 0;
