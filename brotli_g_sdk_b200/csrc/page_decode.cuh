@@ -1,4 +1,5 @@
-// page_decode.cuh -- the Brotli-G page decoder for sm_100a: ONE WARP DECODES ONE PAGE, lane = sub-stream.
+// page_decode.cuh -- the Brotli-G page decoder for sm_100a: TWO WARPS DECODE ONE PAGE (a producer that owns
+// the 32 bit readers, lane = sub-stream, and a consumer that assembles the output).
 //
 // This is a from-scratch CUDA design (not a translation of src/decoder/BrotliGCompute.hlsl). What it
 // has to reproduce bit-for-bit is the behaviour of the reference CPU page decoder:
@@ -8,20 +9,24 @@
 //   BrotligDeswizzler           /root/reference/inc/common/BrotligDeswizzler.h:43-206
 //
 // Design (see DESIGN.md for the full picture):
-//   * per-warp shared-memory arena (WarpSmem, ~13.6 KB): three LSB-first primary look-up tables
-//     (10/10/9 bits) + canonical "limit/base/sorted" arrays for the rare longer codes, a 1 KB literal
-//     ring, and a 4 KB output ring that write-combines the page before it goes to HBM as 16-byte
-//     coalesced stores. Near matches are served from the ring, far matches from L1/L2.
-//   * the bit reader of a lane is a 64-bit window (w0,w1) + one prefetched word, refilled with
-//     aligned 32-bit loads; a peek is a single funnel shift.
+//   * per-page shared-memory arena (WarpSmem, ~13.4 KB, 16 pages resident per SM): three LSB-first primary
+//     look-up tables (9/10/9 bits) + canonical "limit/base/sorted" arrays for the rare longer codes, a
+//     512 B literal ring, a 2 KB output ring that write-combines the page before it goes to HBM as 16-byte
+//     coalesced stores (near matches are served from the ring, far matches from L1/L2), a per-lane cp.async
+//     staging ring for the compressed input and a ring of kQ round buffers between the two warps.
+//   * the bit reader of a lane is a 64-bit window (w0,w1) + one prefetched word, refilled from the staging
+//     ring with one predicated LDS; a peek is a single funnel shift; staging is topped up at a few explicit
+//     places per round.
 //   * table build is warp-parallel: ballot/scan over the run-length coded code lengths, match_any
 //     ranking for the canonical order, cooperative LUT fill for short codes.
-//   * per round of <=32 commands: speculative command decode in every lane, warp scans for output
-//     and literal positions, parallel relaxation of the distance ring, lane-per-command literal
-//     inserts, then match copies in dependency "wavefronts" (a copy runs as soon as its source lies
-//     below the destination of the first still-pending copy).
+//   * PRODUCER, per round of <=32 commands: speculative command decode in every lane, parallel relaxation
+//     of the distance ring, one 64-bit warp scan for output and literal positions, literal decode (two per
+//     peek) into the literal ring; the round is published through an mbarrier.
+//   * CONSUMER, per round: flattened literal inserts (lane t places literal t), then match copies: every
+//     copy whose source is already final goes in one pass flattened over 4-byte pieces (two aligned words +
+//     funnel shift per piece), the few that depend on copies of the same round follow in command order.
 //   * rounds that produce more than kRoundMax bytes or need more literals than the literal ring
-//     holds (long runs) take a warp-cooperative path straight to global memory.
+//     holds (long runs) are executed by the producer straight to global memory.
 //
 // The file is also compiled by g++ against tests/emul/warp_emul.h (BGX_EMULATED) so that the very
 // same code can be exercised on the CPU-only development box. That emulator is test infrastructure.
