@@ -47,7 +47,7 @@
 #endif
 
 #ifndef BGX_WAIT_SLEEP_NS
-#define BGX_WAIT_SLEEP_NS 100
+#define BGX_WAIT_SLEEP_NS 0
 #endif
 #ifndef BGX_RAW_PATH
 #define BGX_RAW_PATH 1
@@ -106,6 +106,7 @@ struct RoundBuf {            // one round of <= 32 commands, producer -> consume
 struct PageCtl {             // hand-over state of the two warps of a page (ordered by the named barriers)
   uint32_t pos, lit_head;        // page position / literal index across a slow round
   uint32_t err, is_delta;
+  uint32_t nslow;                // slow rounds executed so far (phase of the slow_go / slow_done mbarriers)
   uint32_t rflags[kQ];           // per RoundBuf: kFlagLast | kFlagSlow | kFlagAbort
   uint32_t phead[kQ];            // producer only: literal head at the start of the round in that slot
 };
@@ -126,7 +127,7 @@ struct WarpSmem {
                                     // 512 x u16 code-length-code LUT [1024..2047]
   alignas(16) uint4 stage[32][4];   // compressed-input staging: per lane 4 slots x 16 B (cp.async ring)
   RoundBuf rb[kQ];
-  alignas(8) uint64_t mbar[2 * kQ];   // full[kQ], empty[kQ]
+  alignas(8) uint64_t mbar[2 * kQ + 2];   // full[kQ], empty[kQ], slow_go, slow_done
   PageCtl ctl;
 };
 
@@ -587,20 +588,12 @@ BGX_DEV void decode_literals(WarpSmem* sm, BitRd& rd, PageIn& in, uint32_t tail,
 //             to global memory after the consumer has flushed its ring.
 // Every barrier phase is matched (one arrive per sync) so that all barriers are idle again when the page
 // is done -- the CTA is persistent and decodes many pages.
-constexpr uint32_t kBarSlow = 1u;   // named CTA barrier (bar.sync 1, 64) for the slow-round rendezvous; 0 is __syncthreads
-constexpr uint32_t kPageThreadsDev = 64u;
 enum : uint32_t { kFlagLast = 1u, kFlagSlow = 2u, kFlagAbort = 4u };
 
-BGX_DEV void bar_sync_slow() {
-#ifdef BGX_EMULATED
-  wemu::named_bar_sync((int)kBarSlow, (int)kPageThreadsDev);
-#else
-  asm volatile("bar.sync %0, %1;" ::"n"(kBarSlow), "n"(kPageThreadsDev) : "memory");
-#endif
-}
-// full[] / empty[] are mbarriers in shared memory (no per-SM resource besides 8 bytes each): one elected lane
-// arrives (release) after a __syncwarp, every lane of the waiting warp observes the phase (acquire). Round j
-// uses phase j / kQ of slot j mod kQ, so the parity to wait for is (j / kQ) & 1.
+// full[] / empty[] / slow_go / slow_done are mbarriers in shared memory (no per-SM resource besides 8 bytes each;
+// named bar.sync barriers would cap the resident CTAs per SM): one elected lane arrives (release) after a
+// __syncwarp, every lane of the waiting warp observes the phase (acquire). Round j uses phase j / kQ of slot
+// j mod kQ, so the parity to wait for is (j / kQ) & 1; the n-th slow round of a page uses phase n of slow_*.
 BGX_DEV void mbar_init(saddr_t a, uint32_t count) {
 #ifdef BGX_EMULATED
   wemu::mbar_init(reinterpret_cast<uint64_t*>(a), count);
@@ -624,9 +617,9 @@ BGX_DEV void mbar_wait(saddr_t a, uint32_t parity) {
 #ifdef BGX_EMULATED
   wemu::mbar_wait(reinterpret_cast<uint64_t*>(a), parity);
 #else
-  // try_wait suspends the warp for a short, hardware-defined time; a warp that still finds the phase open
-  // backs off with nanosleep instead of spinning (the waiting warp is the one that is ahead: its wake-up
-  // latency hides behind the rounds already queued), so waiting costs next to no issue slots.
+  // try_wait suspends the warp for a short, hardware-defined time before it reports "not yet", so this loop is
+  // not a busy spin. An extra nanosleep back-off (BGX_WAIT_SLEEP_NS > 0) was measured: it changes nothing when
+  // the SM is full and costs single-page latency (each hand-over may then wait out the sleep), so it is off.
   uint32_t done;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -714,7 +707,7 @@ BGX_DEV void producer_warp(const PageJob& job, WarpSmem* sm) {
   if (terr && lane == 0) ctl->err = terr;
   __syncwarp();
 
-  const saddr_t full_a = saddr(sm->mbar), empty_a = full_a + 8u * kQ;
+  const saddr_t full_a = saddr(sm->mbar), empty_a = full_a + 8u * kQ, slow_a = full_a + 16u * kQ;
   uint32_t rnd = 0;            // rounds published so far
   uint32_t synced = 0;         // empty[] phases taken so far: rounds < synced are known to be consumed
   uint32_t lit_tail = 0;       // literals decoded so far
@@ -891,7 +884,9 @@ BGX_DEV void producer_warp(const PageJob& job, WarpSmem* sm) {
       //      consumer has caught up, flushed its ring and published its position.
       if (lane == 0) ctl->rflags[q] = kFlagSlow | (pdone ? kFlagLast : 0u);
       warp_arrive(full_a + 8u * q, lane);
-      bar_sync_slow();
+      const uint32_t nslow = ctl->nslow;       // slow rounds so far = phase of slow_go / slow_done (kept in shared
+                                               // memory: this path is rare and the hot loops are short of registers)
+      mbar_wait(slow_a, nslow & 1u);           // the consumer has flushed its ring and published ctl->pos
       const uint32_t s_ins = ins, s_cpy = cpy, s_n = n, s_round_out = round_out;
       uint32_t s_mine = mine;
       uint32_t p = ctl->pos;
@@ -951,8 +946,9 @@ BGX_DEV void producer_warp(const PageJob& job, WarpSmem* sm) {
         ctl->pos = p;
         ctl->lit_head = lh;
         if (err) ctl->err = err;
+        ctl->nslow = nslow + 1u;
       }
-      bar_sync_slow();
+      warp_arrive(slow_a + 8u, lane);          // slow_done
     }
     ++rnd;
     if (pdone) break;
@@ -974,7 +970,7 @@ BGX_DEV void consumer_warp(const PageJob& job, WarpSmem* sm) {
   bool failed = false;         // a round was rejected: only keep the hand-over going until the producer stops
   const bool out_aligned = (reinterpret_cast<uintptr_t>(out) & 15u) == 0;
   const bool out_al4 = (reinterpret_cast<uintptr_t>(out) & 3u) == 0;
-  const saddr_t full_a = saddr(sm->mbar), empty_a = full_a + 8u * kQ;
+  const saddr_t full_a = saddr(sm->mbar), empty_a = full_a + 8u * kQ, slow_a = full_a + 16u * kQ;
 
   for (uint32_t r = 0;; ++r) {
     const uint32_t q = r & (kQ - 1u);
@@ -982,7 +978,11 @@ BGX_DEV void consumer_warp(const PageJob& job, WarpSmem* sm) {
     const uint32_t rflags = ctl->rflags[q];
     if ((rflags & kFlagAbort) || failed) {
       if (rflags & kFlagAbort) break;
-      if (rflags & kFlagSlow) { bar_sync_slow(); bar_sync_slow(); }   // the producer's rendezvous (it skips the work)
+      if (rflags & kFlagSlow) {   // the producer's rendezvous (it skips the work)
+        const uint32_t nslow = ctl->nslow;
+        warp_arrive(slow_a, lane);
+        mbar_wait(slow_a + 8u, nslow & 1u);
+      }
       warp_arrive(empty_a + 8u * q, lane);
       if (rflags & kFlagLast) break;
       continue;
@@ -990,9 +990,10 @@ BGX_DEV void consumer_warp(const PageJob& job, WarpSmem* sm) {
     if (rflags & kFlagSlow) {
       // ---- slow round: hand a fully flushed page over to the producer, pick it up again afterwards
       flush_bytes(sm, out, flushed, pos, lane);
+      const uint32_t nslow = ctl->nslow;       // read before slow_go: the producer bumps it before slow_done
       if (lane == 0) ctl->pos = pos;
-      bar_sync_slow();
-      bar_sync_slow();
+      warp_arrive(slow_a, lane);               // slow_go: the page is flushed up to ctl->pos
+      mbar_wait(slow_a + 8u, nslow & 1u);      // slow_done
       pos = ctl->pos;
       flushed = pos;
       {   // the ring restarts 4 bytes below the hand-over point, so that flushed >= ring_lo + 4 keeps holding
@@ -1215,9 +1216,10 @@ BGX_DEV_NOINLINE PageResult decode_page_cta(const PageJob& job, WarpSmem* sm) {
   __builtin_assume(__isGlobal(job.in));
 #endif
   if (warp_index() == 0 && lane_id() == 0) {
-    for (uint32_t i = 0; i < 2u * kQ; ++i) mbar_init(saddr(&sm->mbar[i]), 1u);
+    for (uint32_t i = 0; i < 2u * kQ + 2u; ++i) mbar_init(saddr(&sm->mbar[i]), 1u);
     mbar_init_fence();
     sm->ctl.err = 0;
+    sm->ctl.nslow = 0;
   }
   __syncthreads();
   if (warp_index() == 0) producer_warp(job, sm);
@@ -1226,9 +1228,6 @@ BGX_DEV_NOINLINE PageResult decode_page_cta(const PageJob& job, WarpSmem* sm) {
   PageResult res;
   res.status = sm->ctl.err;
   res.is_delta = sm->ctl.is_delta;
-#ifdef BGX_EMULATED
-  if (!wemu::named_bars_idle()) { fprintf(stderr, "decode_page_cta: the slow-round barrier was left pending\n"); abort(); }
-#endif
   __syncthreads();     // everybody has read the result before the page arena is reused
   return res;
 }

@@ -10,9 +10,12 @@ from brotli_g_sdk_b200 import datagen
 
 total = int(sys.argv[1]) << 20 if len(sys.argv) > 1 else 256 << 20
 dec = bg.BrotligDecoder(0)
-data = datagen.mixed(64 << 20, seed=datagen.SEED_CONFIG4)
+kind = sys.argv[2] if len(sys.argv) > 2 else "mixed"
+sizes = tuple(int(x) for x in sys.argv[3].split(",")) if len(sys.argv) > 3 else (4096, 8192, 16384, 32768, 65536, 131072)
+gen = {"mixed": datagen.mixed, "text": datagen.text_like, "binary": datagen.structured_binary, "lowent": datagen.low_entropy}[kind]
+data = gen(64 << 20, seed=datagen.SEED_CONFIG4)
 res = {}
-for ps in (4096, 8192, 16384, 32768, 65536, 131072):
+for ps in sizes:
     if ps >= 32768:
         streams = [bg.Encode(data, page_size=ps)]
         usizes = [len(data)]
