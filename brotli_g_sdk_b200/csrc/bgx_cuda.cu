@@ -179,6 +179,8 @@ struct bgx_context {
   size_t d_in_cap = 0;
   uint8_t* d_out = nullptr;
   size_t d_out_cap = 0;
+  uint8_t* d_scratch = nullptr;   // conditioned planes of texture streams decoded through the host-pointer calls
+  size_t d_scratch_cap = 0;
 };
 
 struct PreconJob {
@@ -199,7 +201,9 @@ struct bgx_plan {
   uint32_t total_pages = 0;
   std::vector<PreconJob> precon;
   uint8_t* d_scratch = nullptr;   // backing store of all conditioned scratch planes
+  bool owns_scratch = true;       // false: borrowed from the context's grow-only arena (host-pointer calls)
   PreconDev* d_precon = nullptr;  // device copy of the pre-conditioned jobs, in stream order
+  PreconLayout* d_layouts = nullptr;   // their layouts, one array
   bgx_plan_info info{};
   cudaStream_t last_stream = nullptr;
   std::vector<uint32_t> q_start;  // [n+1]: first queue slot of caller stream i (prefix sum of its page count)
@@ -290,6 +294,7 @@ void bgx_destroy(bgx_context* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->d_in) cudaFree(ctx->d_in);
   if (ctx->d_out) cudaFree(ctx->d_out);
+  if (ctx->d_scratch) cudaFree(ctx->d_scratch);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -305,16 +310,15 @@ void bgx_plan_destroy(bgx_plan* plan) {
   if (plan->d_streams) cudaFree(plan->d_streams);
   if (plan->d_ctl) cudaFree(plan->d_ctl);
   if (plan->d_status) cudaFree(plan->d_status);
-  if (plan->d_scratch) cudaFree(plan->d_scratch);
+  if (plan->d_scratch && plan->owns_scratch) cudaFree(plan->d_scratch);
   if (plan->d_precon) cudaFree(plan->d_precon);
-  for (auto& p : plan->precon)
-    if (p.d_layout) cudaFree(p.d_layout);
+  if (plan->d_layouts) cudaFree(plan->d_layouts);
   delete plan;
 }
 
 void bgx_plan_get_info(const bgx_plan* plan, bgx_plan_info* info) { *info = plan->info; }
 
-int bgx_plan_create(bgx_context* ctx, const bgx_stream* streams, uint32_t n, bgx_plan** out) {
+static int plan_create_impl(bgx_context* ctx, const bgx_stream* streams, uint32_t n, bgx_plan** out, bool ctx_scratch) {
   *out = nullptr;
   BGX_CUDA(ctx, cudaSetDevice(ctx->device));
   bgx_plan* plan = new bgx_plan();
@@ -389,7 +393,13 @@ int bgx_plan_create(bgx_context* ctx, const bgx_stream* streams, uint32_t n, bgx
   }
   plan->info.pages = plan->total_pages;
   if (scratch_bytes) {
-    BGX_CUDA(ctx, cudaMalloc(&plan->d_scratch, scratch_bytes));
+    if (ctx_scratch) {
+      if (grow(ctx, &ctx->d_scratch, &ctx->d_scratch_cap, scratch_bytes)) return bgx::kErrGeneric;
+      plan->d_scratch = ctx->d_scratch;
+      plan->owns_scratch = false;
+    } else {
+      BGX_CUDA(ctx, cudaMalloc(&plan->d_scratch, scratch_bytes));
+    }
     for (auto& d : plan->h_streams) {
       if (d.allow_delta >> 8) {
         const size_t k = (d.allow_delta >> 8) - 1;
@@ -398,10 +408,15 @@ int bgx_plan_create(bgx_context* ctx, const bgx_stream* streams, uint32_t n, bgx
         d.allow_delta = 1;
       }
     }
+    // all texture layouts of the plan in one device array (one allocation, one copy)
+    std::vector<PreconLayout> hl;
+    for (auto& p : plan->precon) hl.push_back(p.layout);
+    BGX_CUDA(ctx, cudaMalloc(&plan->d_layouts, hl.size() * sizeof(PreconLayout)));
+    BGX_CUDA(ctx, cudaMemcpy(plan->d_layouts, hl.data(), hl.size() * sizeof(PreconLayout), cudaMemcpyHostToDevice));
     std::vector<PreconDev> hj;
-    for (auto& p : plan->precon) {
-      BGX_CUDA(ctx, cudaMalloc(&p.d_layout, sizeof(PreconLayout)));
-      BGX_CUDA(ctx, cudaMemcpy(p.d_layout, &p.layout, sizeof(PreconLayout), cudaMemcpyHostToDevice));
+    for (size_t k = 0; k < plan->precon.size(); ++k) {
+      PreconJob& p = plan->precon[k];
+      p.d_layout = plan->d_layouts + k;
       hj.push_back(PreconDev{p.d_layout, p.d_planes, p.d_tex});
     }
     BGX_CUDA(ctx, cudaMalloc(&plan->d_precon, hj.size() * sizeof(PreconDev)));
@@ -422,6 +437,10 @@ int bgx_plan_create(bgx_context* ctx, const bgx_stream* streams, uint32_t n, bgx
   guard.p = nullptr;
   *out = plan;
   return bgx::kOk;
+}
+
+int bgx_plan_create(bgx_context* ctx, const bgx_stream* streams, uint32_t n, bgx_plan** out) {
+  return plan_create_impl(ctx, streams, n, out, false);
 }
 
 // Enqueues the decode of caller streams [a, b) on `st`, using work-queue control block `group`.
@@ -506,7 +525,7 @@ int bgx_decode_batch_host(bgx_context* ctx, uint32_t n, const uint8_t* const* in
     memcpy(s.header, inputs[i], std::min<uint32_t>(16, input_sizes[i]));
   }
   bgx_plan* plan = nullptr;
-  int rc = bgx_plan_create(ctx, st.data(), n, &plan);
+  int rc = plan_create_impl(ctx, st.data(), n, &plan, true);   // scratch planes from the context's arena
   if (rc) return rc;
   // Three-stage pipeline over groups of streams: upload (s_in) -> kernels (ctx->stream) -> download (s_out).
   // Uploads and downloads run concurrently on the two PCIe directions; the reference host serialises
