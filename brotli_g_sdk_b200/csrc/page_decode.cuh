@@ -26,7 +26,7 @@
 //     copy whose source is already final goes in one pass flattened over 4-byte pieces (two aligned words +
 //     funnel shift per piece), the few that depend on copies of the same round follow in command order.
 //   * rounds that produce more than kRoundMax bytes or need more literals than the literal ring
-//     holds (long runs) are executed by the producer straight to global memory.
+//     holds (long runs) are split by the producer into virtual rounds that fit.
 //
 // The file is also compiled by g++ against tests/emul/warp_emul.h (BGX_EMULATED) so that the very
 // same code can be exercised on the CPU-only development box. That emulator is test infrastructure.
@@ -77,6 +77,7 @@ constexpr uint32_t kLitQ = 512;       // literal ring bytes (power of two): two 
 #endif
 constexpr uint32_t kRing = BGX_RING;      // output ring bytes (power of two, >= kFlushChunk + kRoundMax)
 constexpr uint32_t kRoundMax = 1024;  // largest round (bytes produced) the ring path accepts
+constexpr uint32_t kSplitLits = 256;  // literals per virtual round when a long round is split (two fit the literal ring)
 constexpr uint32_t kFlushChunk = 512; // 32 lanes x 16 B
 constexpr uint32_t kCoopLen = 32;     // inserts/copies at least this long are done by the whole warp
 constexpr uint16_t kLongCode = 0xffffu;  // primary-LUT marker: code longer than the LUT index
@@ -104,10 +105,8 @@ struct RoundBuf {            // one round of <= 32 commands, producer -> consume
   uint32_t pk[32];           //   inclusive prefix sums over the commands: bytes produced | literals consumed << 16
 };
 struct PageCtl {             // hand-over state of the two warps of a page (ordered by the named barriers)
-  uint32_t pos, lit_head;        // page position / literal index across a slow round
   uint32_t err, is_delta;
-  uint32_t nslow;                // slow rounds executed so far (phase of the slow_go / slow_done mbarriers)
-  uint32_t rflags[kQ];           // per RoundBuf: kFlagLast | kFlagSlow | kFlagAbort
+  uint32_t rflags[kQ];           // per RoundBuf: kFlagLast | kFlagAbort
   uint32_t phead[kQ];            // producer only: literal head at the start of the round in that slot
 };
 
@@ -127,7 +126,7 @@ struct WarpSmem {
                                     // 512 x u16 code-length-code LUT [1024..2047]
   alignas(16) uint4 stage[32][4];   // compressed-input staging: per lane 4 slots x 16 B (cp.async ring)
   RoundBuf rb[kQ];
-  alignas(8) uint64_t mbar[2 * kQ + 2];   // full[kQ], empty[kQ], slow_go, slow_done
+  alignas(8) uint64_t mbar[2 * kQ];   // full[kQ], empty[kQ]
   PageCtl ctl;
 };
 
@@ -579,21 +578,20 @@ BGX_DEV void decode_literals(WarpSmem* sm, BitRd& rd, PageIn& in, uint32_t tail,
 //           round in a RoundBuf;
 //   warp 1, the CONSUMER: places literals and match copies in the output ring and streams the page to HBM.
 // The two roles are separate loops (each warp only keeps its own state in registers). Rounds travel
-// through a ring of kQ RoundBufs guarded by named CTA barriers (PTX bar.sync / bar.arrive), so that
-// neither warp polls and the producer may run up to kQ rounds ahead:
-//   full[q]   the producer ARRIVES after publishing round r (q = r mod kQ); the consumer SYNCs before reading it
+// through a ring of kQ RoundBufs guarded by mbarriers in shared memory, so that neither warp executes a CTA-wide
+// barrier inside a page and the producer may run up to kQ rounds ahead:
+//   full[q]   the producer ARRIVES after publishing round r (q = r mod kQ); the consumer WAITs before reading it
 //   empty[q]  the consumer ARRIVES once it no longer needs the round's RoundBuf and literals; the producer
-//             SYNCs on it before it reuses the slot (and earlier, when the literal ring is short of room)
-//   slow      two rendezvous around a round with long runs ("slow"), which the producer executes straight
-//             to global memory after the consumer has flushed its ring.
-// Every barrier phase is matched (one arrive per sync) so that all barriers are idle again when the page
-// is done -- the CTA is persistent and decodes many pages.
-enum : uint32_t { kFlagLast = 1u, kFlagSlow = 2u, kFlagAbort = 4u };
+//             WAITs on it before it reuses the slot (and earlier, when the literal ring is short of room)
+// A round with long runs (more than kRoundMax bytes, or more literals than the literal ring holds) travels as a
+// sequence of "virtual" rounds that each fit (see the producer), so the consumer only ever sees one kind of round.
+// The mbarriers are re-initialised at the start of every page (the CTA is persistent and decodes many pages).
+enum : uint32_t { kFlagLast = 1u, kFlagAbort = 4u };
 
-// full[] / empty[] / slow_go / slow_done are mbarriers in shared memory (no per-SM resource besides 8 bytes each;
+// full[] / empty[] are mbarriers in shared memory (no per-SM resource besides 8 bytes each;
 // named bar.sync barriers would cap the resident CTAs per SM): one elected lane arrives (release) after a
 // __syncwarp, every lane of the waiting warp observes the phase (acquire). Round j uses phase j / kQ of slot
-// j mod kQ, so the parity to wait for is (j / kQ) & 1; the n-th slow round of a page uses phase n of slow_*.
+// j mod kQ, so the parity to wait for is (j / kQ) & 1.
 BGX_DEV void mbar_init(saddr_t a, uint32_t count) {
 #ifdef BGX_EMULATED
   wemu::mbar_init(reinterpret_cast<uint64_t*>(a), count);
@@ -648,14 +646,13 @@ BGX_DEV void producer_warp(const PageJob& job, WarpSmem* sm) {
   const uint32_t lane = lane_id();
   const uint32_t lt_mask = (1u << lane) - 1u;
   PageCtl* ctl = &sm->ctl;
-  uint8_t* const out = job.out;
   const uint32_t out_size = job.out_size;
 
   PageIn in;
   BitRd rd;
   uint32_t npostfix = 0, ndirect = 0;
   if (lane == 0) {
-    ctl->pos = 0; ctl->lit_head = 0; ctl->is_delta = 0;
+    ctl->is_delta = 0;
   }
   in.base = reinterpret_cast<const uint32_t*>(job.in);
   in.lim = (job.in_limit >> 2) ? (job.in_limit >> 2) - 1 : 0;
@@ -707,25 +704,53 @@ BGX_DEV void producer_warp(const PageJob& job, WarpSmem* sm) {
   if (terr && lane == 0) ctl->err = terr;
   __syncwarp();
 
-  const saddr_t full_a = saddr(sm->mbar), empty_a = full_a + 8u * kQ, slow_a = full_a + 16u * kQ;
+  const saddr_t full_a = saddr(sm->mbar), empty_a = full_a + 8u * kQ;
   uint32_t rnd = 0;            // rounds published so far
   uint32_t synced = 0;         // empty[] phases taken so far: rounds < synced are known to be consumed
   uint32_t lit_tail = 0;       // literals decoded so far
   uint32_t lit_head_p = 0;     // literals that the rounds published so far consume
   uint32_t r0 = 4, r1 = 11, r2 = 15, r3 = 16;   // distance ring (PageDecoder.cpp:150-153)
   bool pdone = false;
-  for (;;) {
+  uint32_t pos_p = 0;          // bytes the rounds published so far produce
+  // waits until slot rnd % kQ is free; false when the page is being aborted (the abort round is then published)
+  auto acquire_slot = [&]() -> bool {
     const uint32_t q = rnd & (kQ - 1u);
-    while (synced + kQ <= rnd) {   // slot q still holds round rnd - kQ: wait until the consumer is done with it
+    while (synced + kQ <= rnd) {   // the slot still holds round rnd - kQ: wait until the consumer is done with it
       mbar_wait(empty_a + 8u * (synced & (kQ - 1u)), (synced / kQ) & 1u);
       ++synced;
     }
     if (ld_volatile_u32(&ctl->err)) {   // a table error, or the consumer rejected a round: tell it to stop
       if (lane == 0) ctl->rflags[q] = kFlagAbort;
       warp_arrive(full_a + 8u * q, lane);
-      break;
+      return false;
     }
+    return true;
+  };
+  // the literal ring must hold `newlits` more literals next to those of every round the consumer may still be
+  // working on (rounds >= synced): takes more empty[] phases while that helps; false if they cannot fit at all
+  auto wait_lit_room = [&](uint32_t newlits) -> bool {
+    uint32_t head_known = synced == rnd ? lit_head_p : ctl->phead[synced & (kQ - 1u)];
+    bool fits = (lit_tail - head_known) + newlits <= kLitQ;
+    while (!fits && synced < rnd) {
+      mbar_wait(empty_a + 8u * (synced & (kQ - 1u)), (synced / kQ) & 1u);
+      ++synced;
+      head_known = synced == rnd ? lit_head_p : ctl->phead[synced & (kQ - 1u)];
+      fits = (lit_tail - head_known) + newlits <= kLitQ;
+    }
+    return fits;
+  };
+  auto publish = [&](uint32_t dxv, uint32_t pkv, uint32_t flags) {
+    const uint32_t q = rnd & (kQ - 1u);
     RoundBuf* rb = &sm->rb[q];
+    rb->dx[lane] = dxv;            // final distance
+    rb->pk[lane] = pkv;            // inclusive sums: output | literals << 16
+    if (lane == 0) ctl->rflags[q] = flags;
+    warp_arrive(full_a + 8u * q, lane);
+    ++rnd;
+  };
+  for (;;) {
+    if (!acquire_slot()) break;
+    const uint32_t q = rnd & (kQ - 1u);
     br_topup1(rd, in);
     // ---- one command per lane, speculatively (lanes after the sentinel roll back)
     BitRd r = rd;
@@ -858,99 +883,80 @@ BGX_DEV void producer_warp(const PageJob& job, WarpSmem* sm) {
     const uint32_t mult = n ? (n == 32u ? (need + 31u) >> 5 : (need + n - 1u) / n) : 0u;
     const uint32_t rl = n * mult;                     // literals the stream carries for this round
     uint32_t mine = rl > lane ? (rl - lane + 31u) >> 5 : 0u;   // literal indices lit_tail + j*32 + lane
-    // the literal ring must hold this round's literals next to those of every round the consumer may still
-    // be working on: rounds >= synced. Take more empty[] phases while that helps.
-    uint32_t head_known = synced == rnd ? lit_head_p : ctl->phead[synced & (kQ - 1u)];
-    bool fits = (lit_tail - head_known) + rl <= kLitQ;
-    while (!fits && synced < rnd) {
-      mbar_wait(empty_a + 8u * (synced & (kQ - 1u)), (synced / kQ) & 1u);
-      ++synced;
-      head_known = synced == rnd ? lit_head_p : ctl->phead[synced & (kQ - 1u)];
-      fits = (lit_tail - head_known) + rl <= kLitQ;
+    // a producer-side position check bounds the work a corrupt stream can ask for (the consumer checks too)
+    pos_p += round_out;
+    if (round_out > out_size || pos_p > out_size) {
+      if (lane == 0) { ctl->err = kPageErrOverrun; ctl->rflags[q] = kFlagAbort; }
+      warp_arrive(full_a + 8u * q, lane);
+      break;
     }
-    const bool fast = round_out <= kRoundMax && fits;
+    bool fast = round_out <= kRoundMax && rl <= kLitQ;
+    if (fast) fast = wait_lit_room(rl);
     BGX_STAT(emu_stats().rounds++; emu_stats().lits += rl; if (!fast) emu_stats().slow_rounds++);
-    if (lane == 0) ctl->phead[q] = lit_head_p;   // literal head at the start of this round
     if (fast) {
+      if (lane == 0) ctl->phead[q] = lit_head_p;   // literal head at the start of this round
       decode_literals(sm, rd, in, lit_tail, mine, lane);
       lit_tail += rl;
       lit_head_p += round_ins;
-      rb->dx[lane] = dx;            // final distance
-      rb->pk[lane] = (uint32_t)(incl_both >> 32) | ((uint32_t)incl_both << 16);   // inclusive sums: output | literals << 16
-      if (lane == 0) ctl->rflags[q] = pdone ? kFlagLast : 0u;
-      warp_arrive(full_a + 8u * q, lane);
+      publish(dx, (uint32_t)(incl_both >> 32) | ((uint32_t)incl_both << 16), pdone ? kFlagLast : 0u);
     } else {
-      // ---- slow round (long runs): executed here, straight to global memory, command by command, once the
-      //      consumer has caught up, flushed its ring and published its position.
-      if (lane == 0) ctl->rflags[q] = kFlagSlow | (pdone ? kFlagLast : 0u);
-      warp_arrive(full_a + 8u * q, lane);
-      const uint32_t nslow = ctl->nslow;       // slow rounds so far = phase of slow_go / slow_done (kept in shared
-                                               // memory: this path is rare and the hot loops are short of registers)
-      mbar_wait(slow_a, nslow & 1u);           // the consumer has flushed its ring and published ctl->pos
-      const uint32_t s_ins = ins, s_cpy = cpy, s_n = n, s_round_out = round_out;
-      uint32_t s_mine = mine;
-      uint32_t p = ctl->pos;
-      uint32_t lh = lit_head_p;
-      uint32_t err = ld_volatile_u32(&ctl->err);   // (the consumer may have rejected an earlier round)
-      if (!err && s_round_out > out_size - p) err = kPageErrOverrun;
-      for (uint32_t k = 0; k < s_n && !err; ++k) {
-        uint32_t n_ins = __shfl_sync(kFull, s_ins, (int)k);
-        const uint32_t n_cpy = __shfl_sync(kFull, s_cpy, (int)k);
-        const uint32_t d_k = __shfl_sync(kFull, dx, (int)k);
-        if (n_cpy && (d_k == 0 || d_k > p + n_ins)) { err = kPageErrDistance; break; }
-        while (n_ins) {
-          uint32_t have = lit_tail - lh;
-          if (have == 0) {
-            // decode the next chunk of this round's literals (as many as the literal ring takes)
-            const uint32_t room = kLitQ >> 5;
-            const uint32_t c = s_mine < room ? s_mine : room;
-            const uint32_t total = __reduce_add_sync(kFull, c);
-            if (total == 0) { err = kPageErrLiterals; break; }
-            decode_literals(sm, rd, in, lit_tail, c, lane);
-            s_mine -= c;
-            lit_tail += total;
-            __syncwarp();
-            have = lit_tail - lh;
-          }
-          const uint32_t take = n_ins < have ? n_ins : have;
-          for (uint32_t j = lane; j < take; j += 32) out[p + j] = sm->litq[(lh + j) & (kLitQ - 1)];
-          p += take;
-          lh += take;
-          n_ins -= take;
-          __syncwarp();
+      // ---- a round with long runs (more output than the ring path takes at once, or more literals than the
+      //      literal ring holds) is handed over as a sequence of VIRTUAL rounds that each fit: a virtual round
+      //      takes as many whole commands as fit, in order, or -- when the next command alone is too big -- a
+      //      piece of it (first <= kSplitLits of its literals at a time, then <= kRoundMax bytes of its copy at a
+      //      time; a copy split in two is the same byte-serial copy, PageDecoder.cpp:222-232). The consumer sees
+      //      ordinary rounds in which the other lanes carry empty commands; the round's literals are decoded
+      //      row by row (32 at a time, all lanes) as the virtual rounds need them.
+      uint32_t rem_ins = ins, rem_cpy = cpy;   // what is left of this lane's command
+      uint32_t s_mine = mine;                  // literals this lane still has to decode in this round
+      bool first = true, aborted = false;
+      for (;;) {
+        const uint32_t work = __ballot_sync(kFull, (rem_ins | rem_cpy) != 0u);
+        if (!first) {
+          if (!acquire_slot()) { aborted = true; break; }
         }
-        if (err) break;
-        if (n_cpy) {
-          const uint32_t s_k = p - d_k;
-          for (uint32_t j = lane; j < n_cpy; j += 32) {
-            const uint32_t m = j < d_k ? j : j % d_k;
-            out[p + j] = out[s_k + m];
-          }
-          p += n_cpy;
-          __syncwarp();
+        first = false;
+        const uint32_t qv = rnd & (kQ - 1u);
+        const uint32_t a0 = work ? (uint32_t)(__ffs((int)work) - 1) : 32u;   // first command with something left
+        uint32_t v_ins = rem_ins, v_cpy = rem_cpy;
+        if (lane == a0) {                        // the leading command may have to be clipped
+          if (v_ins > kSplitLits) { v_ins = kSplitLits; v_cpy = 0; }
+          else if (v_cpy > kRoundMax - v_ins) v_cpy = kRoundMax - v_ins;
         }
-      }
-      // literals the round still carries (decoded ahead of need, at most 31 remain unused)
-      while (!err && __reduce_add_sync(kFull, s_mine) != 0) {
-        const uint32_t room = (kLitQ - (lit_tail - lh)) >> 5;
-        const uint32_t c = s_mine < room ? s_mine : room;
+        const bool clipped = __ballot_sync(kFull, lane == a0 && (v_ins != rem_ins || v_cpy != rem_cpy)) != 0u;
+        const uint64_t vincl = warp_incl_scan64(((uint64_t)(v_ins + v_cpy) << 32) | v_ins, lane);
+        const bool ok = (uint32_t)(vincl >> 32) <= kRoundMax && (uint32_t)vincl <= kSplitLits;
+        const uint32_t notok = ~__ballot_sync(kFull, ok) & ~(0xffffffffu >> (31u - (a0 & 31u)));   // lanes > a0 that do not fit
+        const uint32_t b0 = a0 >= 32u ? 32u : clipped ? a0 + 1u : (notok ? (uint32_t)(__ffs((int)notok) - 1) : 32u);
+        if (lane >= b0) { v_ins = 0; v_cpy = 0; }
+        const uint64_t vtot = __shfl_sync(kFull, vincl, (int)((b0 ? b0 : 1u) - 1u));   // sums over the taken commands
+        const uint64_t vpk = lane < b0 ? vincl : vtot;
+        const uint32_t vr_ins = (uint32_t)vtot;
+        rem_ins -= v_ins;
+        rem_cpy -= v_cpy;
+        const bool last_virtual = __ballot_sync(kFull, (rem_ins | rem_cpy) != 0u) == 0u;
+        // literals: whole rows until the virtual round is covered; everything the round still carries with the last one
+        const uint32_t have = lit_tail - lit_head_p;
+        const uint32_t want = vr_ins > have ? vr_ins - have : 0u;
+        const uint32_t rows = (want + 31u) >> 5;
+        const uint32_t c = last_virtual ? s_mine : (s_mine < rows ? s_mine : rows);
         const uint32_t total = __reduce_add_sync(kFull, c);
-        if (total == 0) { err = kPageErrLiterals; break; }
+        if (have + total < vr_ins || !wait_lit_room(total)) {   // the stream does not carry the literals it inserts
+          if (lane == 0) { ctl->err = kPageErrLiterals; ctl->rflags[qv] = kFlagAbort; }
+          warp_arrive(full_a + 8u * qv, lane);
+          aborted = true;
+          break;
+        }
+        if (lane == 0) ctl->phead[qv] = lit_head_p;
         decode_literals(sm, rd, in, lit_tail, c, lane);
         s_mine -= c;
         lit_tail += total;
-        __syncwarp();
+        lit_head_p += vr_ins;
+        publish(dx, (uint32_t)(vpk >> 32) | ((uint32_t)vpk << 16), (last_virtual && pdone) ? kFlagLast : 0u);
+        if (last_virtual) break;
       }
-      lit_head_p = lh;
-      if (lane == 0) {
-        ctl->pos = p;
-        ctl->lit_head = lh;
-        if (err) ctl->err = err;
-        ctl->nslow = nslow + 1u;
-      }
-      warp_arrive(slow_a + 8u, lane);          // slow_done
+      if (aborted) break;
     }
-    ++rnd;
     if (pdone) break;
   }
 }
@@ -970,7 +976,7 @@ BGX_DEV void consumer_warp(const PageJob& job, WarpSmem* sm) {
   bool failed = false;         // a round was rejected: only keep the hand-over going until the producer stops
   const bool out_aligned = (reinterpret_cast<uintptr_t>(out) & 15u) == 0;
   const bool out_al4 = (reinterpret_cast<uintptr_t>(out) & 3u) == 0;
-  const saddr_t full_a = saddr(sm->mbar), empty_a = full_a + 8u * kQ, slow_a = full_a + 16u * kQ;
+  const saddr_t full_a = saddr(sm->mbar), empty_a = full_a + 8u * kQ;
 
   for (uint32_t r = 0;; ++r) {
     const uint32_t q = r & (kQ - 1u);
@@ -978,36 +984,8 @@ BGX_DEV void consumer_warp(const PageJob& job, WarpSmem* sm) {
     const uint32_t rflags = ctl->rflags[q];
     if ((rflags & kFlagAbort) || failed) {
       if (rflags & kFlagAbort) break;
-      if (rflags & kFlagSlow) {   // the producer's rendezvous (it skips the work)
-        const uint32_t nslow = ctl->nslow;
-        warp_arrive(slow_a, lane);
-        mbar_wait(slow_a + 8u, nslow & 1u);
-      }
       warp_arrive(empty_a + 8u * q, lane);
       if (rflags & kFlagLast) break;
-      continue;
-    }
-    if (rflags & kFlagSlow) {
-      // ---- slow round: hand a fully flushed page over to the producer, pick it up again afterwards
-      flush_bytes(sm, out, flushed, pos, lane);
-      const uint32_t nslow = ctl->nslow;       // read before slow_go: the producer bumps it before slow_done
-      if (lane == 0) ctl->pos = pos;
-      warp_arrive(slow_a, lane);               // slow_go: the page is flushed up to ctl->pos
-      mbar_wait(slow_a + 8u, nslow & 1u);      // slow_done
-      pos = ctl->pos;
-      flushed = pos;
-      {   // the ring restarts 4 bytes below the hand-over point, so that flushed >= ring_lo + 4 keeps holding
-        const uint32_t back = pos < 4u ? pos : 4u;
-        if (lane < back) sm->ring[(pos - back + lane) & (kRing - 1)] = out[pos - back + lane];
-        ring_from = (int32_t)(pos - back);
-        __syncwarp();
-      }
-      lit_head = ctl->lit_head;
-      warp_arrive(empty_a + 8u * q, lane);
-      if (rflags & kFlagLast) {
-        for (uint32_t z = pos + lane; z < out_size; z += 32) out[z] = 0;
-        break;
-      }
       continue;
     }
     const RoundBuf* rb = &sm->rb[q];
@@ -1216,10 +1194,9 @@ BGX_DEV_NOINLINE PageResult decode_page_cta(const PageJob& job, WarpSmem* sm) {
   __builtin_assume(__isGlobal(job.in));
 #endif
   if (warp_index() == 0 && lane_id() == 0) {
-    for (uint32_t i = 0; i < 2u * kQ + 2u; ++i) mbar_init(saddr(&sm->mbar[i]), 1u);
+    for (uint32_t i = 0; i < 2u * kQ; ++i) mbar_init(saddr(&sm->mbar[i]), 1u);
     mbar_init_fence();
     sm->ctl.err = 0;
-    sm->ctl.nslow = 0;
   }
   __syncthreads();
   if (warp_index() == 0) producer_warp(job, sm);

@@ -169,6 +169,32 @@ def test_full_size_random_buffer_checksum_of_checksums(sdk, dec):
         assert zlib.crc32(o.tobytes()) == zlib.crc32(d.tobytes())
 
 
+def test_full_size_mixed_entropy_batch_is_bit_exact(sdk, dec):
+    """BASELINE config 4 shape (64 MiB mixed-entropy streams: compressed and raw pages side by side), 256 MiB
+    here, decoded in one device-resident launch: every stream equals its source byte for byte (the oracle
+    is too slow at this size; the source is the ground truth the oracle is pinned to)"""
+    import torch
+    from brotli_g_sdk_b200 import datagen
+    keep, descs, sources = [], [], []
+    for i in range(4):
+        d = datagen.mixed(64 << 20, seed=datagen.SEED_CONFIG4 + 7 * i)
+        s = sdk.Encode(d)
+        assert len(s) < len(d)
+        t_in = torch.zeros(len(s) + 64, dtype=torch.uint8, device="cuda")
+        t_in[: len(s)] = torch.from_numpy(s).cuda()
+        t_out = torch.full((len(d),), 0xEE, dtype=torch.uint8, device="cuda")
+        keep.append((t_in, t_out))
+        sources.append(d)
+        descs.append(dict(d_src=t_in.data_ptr(), src_size=len(s), src_capacity=len(s) + 64, d_dst=t_out.data_ptr(),
+                          dst_capacity=len(d), header=bytes(s[:16])))
+    plan = dec.plan(descs)
+    for _ in range(2):      # a second launch over the same plan: the persistent CTAs leave no state behind
+        plan.launch(torch.cuda.current_stream().cuda_stream)
+        assert plan.finish() == 0
+    for (t_in, t_out), d in zip(keep, sources):
+        assert torch.equal(t_out.cpu(), torch.from_numpy(d)), "GPU output != source bytes"
+
+
 def test_page_size_sweep_small_single_page_streams(sdk, oracle, dec):
     """config 5: 4/8/16 KiB "pages" are single-page streams (NumPages = 1, LastPageSize = n)"""
     from brotli_g_sdk_b200 import datagen
