@@ -63,6 +63,21 @@ def corner_cases() -> dict:
     for np_ in range(4):
         for nd in (0, 15):
             c[f"npostfix{np_}_ndirect{nd}"] = (ring_code_workout(70000, 20 + np_), dict(npostfix=np_, ndirect_msb=nd))
+    # rounds made of many big commands: every command inserts hundreds of literals and copies a little (the page kernel
+    # splits such rounds into virtual rounds: whole commands, then pieces of one command)
+    rr = _rng(0xB16)
+    key = rr.integers(0, 256, 64, dtype=np.uint8)
+    parts = []
+    for i in range(90):
+        parts += [rr.integers(0, 256, int(rr.integers(300, 1500)), dtype=np.uint8), key[: int(rr.integers(8, 64))]]
+    c["big_inserts_small_copies"] = (np.concatenate(parts), {})
+    # ... and the mirror image: a few literals, then kilobytes copied from far back (copies longer than a round takes)
+    base = rr.integers(0, 256, 9000, dtype=np.uint8)
+    parts = [base]
+    for i in range(40):
+        o = int(rr.integers(0, 4000))
+        parts += [rr.integers(0, 256, int(rr.integers(1, 6)), dtype=np.uint8), base[o: o + int(rr.integers(1100, 4800))]]
+    c["small_inserts_big_copies"] = (np.concatenate(parts), {})
     c["no_ring_codes"] = (datagen.text_like(80000, seed=30), dict(use_ring_codes=0))
     c["greedy_short_chain"] = (datagen.text_like(80000, seed=31), dict(lazy=0, max_chain=1))
     return c
