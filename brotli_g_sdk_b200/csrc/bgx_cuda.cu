@@ -496,17 +496,15 @@ int bgx_plan_finish(bgx_context* ctx, bgx_plan* plan, uint32_t* bad_pages) {
 int bgx_decode_batch_host(bgx_context* ctx, uint32_t n, const uint8_t* const* inputs, const uint32_t* input_sizes,
                           uint8_t* const* outputs, uint32_t* output_sizes, double* kernel_ms) {
   BGX_CUDA(ctx, cudaSetDevice(ctx->device));
-  std::vector<bgx_stream> st(n);
+  std::vector<StreamInfo> info(n);
   std::vector<size_t> in_off(n), out_off(n);
-  std::vector<uint32_t> usize(n);
   size_t in_total = 0, out_total = 0;
   for (uint32_t i = 0; i < n; ++i) {
     if (input_sizes[i] < bgx::kStreamHeaderBytes) { ctx->err = "stream shorter than its header"; return bgx::kErrCorruptStream; }
-    StreamInfo si;
+    StreamInfo& si = info[i];
     const int rc = bgx::parse_stream_header(inputs[i], &si);
     if (rc) return rc;
     if (si.uncompressed_size > output_sizes[i]) { ctx->err = "output buffer too small"; return bgx::kErrGeneric; }
-    usize[i] = si.uncompressed_size;
     in_off[i] = in_total;
     in_total += ((size_t)input_sizes[i] + bgx::kInputSlackBytes + 255u) & ~(size_t)255u;
     out_off[i] = out_total;
@@ -514,30 +512,70 @@ int bgx_decode_batch_host(bgx_context* ctx, uint32_t n, const uint8_t* const* in
   }
   if (grow(ctx, &ctx->d_in, &ctx->d_in_cap, in_total)) return bgx::kErrGeneric;
   if (grow(ctx, &ctx->d_out, &ctx->d_out_cap, out_total)) return bgx::kErrGeneric;
+
+  // Three-stage pipeline: upload (s_in) -> kernels (ctx->stream) -> download (s_out); uploads and downloads run
+  // concurrently on the two PCIe directions (the reference host serialises upload -> dispatch -> readback,
+  // BrotligGPUDecoder.cpp:633-727). The unit of the pipeline is a SEGMENT: a whole stream, or -- for streams that
+  // are large against the batch -- a range of its pages (pages are independent and contiguous in the stream, so a
+  // range needs the stream's bytes up to the end of its last page and produces a contiguous slice of the output).
+  // A single 64 MiB stream therefore overlaps its own upload, decode and download too.
+  struct Segment {
+    uint32_t stream, page_begin, page_count;   // page_count 0 = the whole stream
+    size_t up0, up1;                           // stream bytes [up0, up1) to upload before this segment can run
+    size_t dn0, dn1;                           // output bytes [dn0, dn1) it produces
+  };
+  const size_t total = in_total + out_total;
+  const size_t target = std::max<size_t>(48u << 20, total / 12);   // (finer units measured no faster: PCIe is the bound)
+  std::vector<Segment> seg;
   for (uint32_t i = 0; i < n; ++i) {
-    bgx_stream& s = st[i];
+    const StreamInfo& si = info[i];
+    const size_t bytes = (size_t)input_sizes[i] + si.uncompressed_size;
+    const size_t table_end = (size_t)si.header_bytes + 4ull * si.num_pages;
+    uint32_t parts = (uint32_t)std::min<size_t>((bytes + target - 1) / target, si.num_pages);
+    if (si.preconditioned || parts < 2 || table_end > input_sizes[i]) {   // (a truncated table is reported by the plan)
+      seg.push_back(Segment{i, 0, 0, 0, input_sizes[i], 0, si.uncompressed_size});
+      continue;
+    }
+    const uint32_t per = (si.num_pages + parts - 1) / parts;
+    size_t up_prev = 0;
+    for (uint32_t pb = 0; pb < si.num_pages; pb += per) {
+      const uint32_t pc = std::min(per, si.num_pages - pb);
+      const bool last = pb + pc == si.num_pages;
+      // end of the range's last page inside the stream: page table entry pb + pc (offset from the end of the table)
+      size_t up1 = last ? (size_t)input_sizes[i] : table_end + bgx::load_le32(inputs[i] + si.header_bytes + 4ull * (pb + pc));
+      up1 = std::min<size_t>(std::max(up1, std::max(up_prev, table_end)), input_sizes[i]);   // corrupt tables stay in bounds
+      const size_t dn0 = (size_t)pb * si.page_size;
+      const size_t dn1 = last ? (size_t)si.uncompressed_size : (size_t)(pb + pc) * si.page_size;
+      seg.push_back(Segment{i, pb, pc, up_prev, up1, dn0, dn1});
+      up_prev = up1;
+    }
+  }
+  const uint32_t ns = (uint32_t)seg.size();
+  std::vector<bgx_stream> st(ns);
+  for (uint32_t k = 0; k < ns; ++k) {
+    const Segment& g = seg[k];
+    const uint32_t i = g.stream;
+    bgx_stream& s = st[k];
     memset(&s, 0, sizeof s);
     s.d_src = ctx->d_in + in_off[i];
     s.src_size = input_sizes[i];
     s.src_capacity = (input_sizes[i] + 15u) & ~15u;   // the arena slot has kInputSlackBytes of slack
-    s.d_dst = ctx->d_out + out_off[i];
-    s.dst_capacity = usize[i];
+    s.d_dst = ctx->d_out + out_off[i] + g.dn0;        // where page `page_begin` goes
+    s.dst_capacity = (uint32_t)(g.dn1 - g.dn0);
+    s.page_begin = g.page_begin;
+    s.page_count = g.page_count;
     memcpy(s.header, inputs[i], std::min<uint32_t>(16, input_sizes[i]));
   }
   bgx_plan* plan = nullptr;
-  int rc = plan_create_impl(ctx, st.data(), n, &plan, true);   // scratch planes from the context's arena
+  int rc = plan_create_impl(ctx, st.data(), ns, &plan, true);   // scratch planes from the context's arena
   if (rc) return rc;
-  // Three-stage pipeline over groups of streams: upload (s_in) -> kernels (ctx->stream) -> download (s_out).
-  // Uploads and downloads run concurrently on the two PCIe directions; the reference host serialises
-  // upload -> dispatch -> readback (BrotligGPUDecoder.cpp:633-727).
+  // groups of consecutive segments, each at least `target` bytes (one launch and one event triple per group)
   std::vector<uint32_t> cut{0};
   {
-    const size_t total = in_total + out_total;
-    const size_t target = std::max<size_t>(48u << 20, total / 12);
     size_t acc = 0;
-    for (uint32_t i = 0; i < n; ++i) {
-      acc += (size_t)input_sizes[i] + usize[i];
-      if ((acc >= target && cut.size() < kMaxGroups) || i + 1 == n) { cut.push_back(i + 1); acc = 0; }
+    for (uint32_t k = 0; k < ns; ++k) {
+      acc += (seg[k].up1 - seg[k].up0) + (seg[k].dn1 - seg[k].dn0);
+      if ((acc >= target && cut.size() < kMaxGroups) || k + 1 == ns) { cut.push_back(k + 1); acc = 0; }
     }
   }
   const uint32_t G = (uint32_t)cut.size() - 1;
@@ -551,16 +589,22 @@ int bgx_decode_batch_host(bgx_context* ctx, uint32_t n, const uint8_t* const* in
   cudaStreamWaitEvent(ctx->s_out, ev_start, 0);
   for (uint32_t g = 0; g < G && !rc; ++g) {
     cudaEvent_t e_in = ev[3 * g], e_k0 = ev[3 * g + 1], e_k1 = ev[3 * g + 2];
-    for (uint32_t i = cut[g]; i < cut[g + 1]; ++i)
-      cudaMemcpyAsync(ctx->d_in + in_off[i], inputs[i], input_sizes[i], cudaMemcpyHostToDevice, ctx->s_in);
+    for (uint32_t k = cut[g]; k < cut[g + 1]; ++k) {
+      const Segment& sg = seg[k];
+      if (sg.up1 > sg.up0)
+        cudaMemcpyAsync(ctx->d_in + in_off[sg.stream] + sg.up0, inputs[sg.stream] + sg.up0, sg.up1 - sg.up0, cudaMemcpyHostToDevice, ctx->s_in);
+    }
     cudaEventRecord(e_in, ctx->s_in);
     cudaStreamWaitEvent(ctx->stream, e_in, 0);
     cudaEventRecord(e_k0, ctx->stream);
     rc = launch_range(ctx, plan, cut[g], cut[g + 1], g, ctx->stream);
     cudaEventRecord(e_k1, ctx->stream);
     cudaStreamWaitEvent(ctx->s_out, e_k1, 0);
-    for (uint32_t i = cut[g]; i < cut[g + 1]; ++i)
-      if (usize[i]) cudaMemcpyAsync(outputs[i], ctx->d_out + out_off[i], usize[i], cudaMemcpyDeviceToHost, ctx->s_out);
+    for (uint32_t k = cut[g]; k < cut[g + 1]; ++k) {
+      const Segment& sg = seg[k];
+      if (sg.dn1 > sg.dn0)
+        cudaMemcpyAsync(outputs[sg.stream] + sg.dn0, ctx->d_out + out_off[sg.stream] + sg.dn0, sg.dn1 - sg.dn0, cudaMemcpyDeviceToHost, ctx->s_out);
+    }
   }
   cudaStreamSynchronize(ctx->s_in);
   cudaStreamSynchronize(ctx->s_out);
@@ -573,7 +617,7 @@ int bgx_decode_batch_host(bgx_context* ctx, uint32_t n, const uint8_t* const* in
       if (cudaEventElapsedTime(&ms, ev[3 * g + 1], ev[3 * g + 2]) == cudaSuccess) sum += ms;
     }
     if (kernel_ms) *kernel_ms += sum;
-    for (uint32_t i = 0; i < n; ++i) output_sizes[i] = usize[i];
+    for (uint32_t i = 0; i < n; ++i) output_sizes[i] = info[i].uncompressed_size;
   }
   for (auto& e : ev) cudaEventDestroy(e);
   cudaEventDestroy(ev_start);

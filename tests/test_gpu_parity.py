@@ -195,6 +195,16 @@ def test_full_size_mixed_entropy_batch_is_bit_exact(sdk, dec):
         assert torch.equal(t_out.cpu(), torch.from_numpy(d)), "GPU output != source bytes"
 
 
+def test_single_large_stream_through_the_host_call(sdk, dec):
+    """DecodeGPU of ONE 64 MiB mixed-entropy stream: the host-pointer path splits it into page ranges that are
+    uploaded, decoded and downloaded as a pipeline; the result must not depend on that"""
+    from brotli_g_sdk_b200 import datagen
+    d = datagen.mixed(64 << 20, seed=datagen.SEED_CONFIG4 + 99)
+    s = sdk.Encode(d)
+    out, ms = dec.decode_host(s)
+    assert ms > 0 and np.array_equal(out, d), "host-pointer decode of a large stream != source bytes"
+
+
 def test_page_size_sweep_small_single_page_streams(sdk, oracle, dec):
     """config 5: 4/8/16 KiB "pages" are single-page streams (NumPages = 1, LastPageSize = n)"""
     from brotli_g_sdk_b200 import datagen
