@@ -2,6 +2,8 @@
 Each entry: name -> (data, encoder kwargs). Shared by the oracle, emulator and GPU parity tests."""
 from __future__ import annotations
 
+import functools
+
 import numpy as np
 
 from brotli_g_sdk_b200 import datagen
@@ -18,18 +20,42 @@ def ring_code_workout(n: int, seed: int) -> np.ndarray:
     out = [base]
     total = len(base)
     dists = [17, 64, 129, 255]
+    buf = base[-300:]                      # the last <= 300 bytes produced so far
     while total < n:
         d = dists[int(r.integers(0, 4))] + int(r.integers(-3, 4))
         l = int(r.integers(3, 40))
-        buf = np.concatenate(out)[-300:]
         d = max(1, min(d, len(buf)))
         seg = np.array([buf[len(buf) - d + (k % d)] for k in range(l)], dtype=np.uint8)
         lit = r.integers(0, 256, size=int(r.integers(0, 4)), dtype=np.uint8)
         out += [seg, lit]
         total += l + len(lit)
+        buf = np.concatenate([buf, seg, lit])[-300:]
     return np.concatenate(out)[:n].copy()
 
 
+def run_structure_fuzz(n: int, seed: int) -> np.ndarray:
+    """literal runs and copies whose lengths sit on and around the page kernel's hand-over limits (256 literals per
+    virtual round, 1024 bytes per round, 512-byte literal ring, 32-byte rows), near and far, some overlapping"""
+    r = _rng(seed)
+    edges = np.array([1, 2, 3, 31, 32, 33, 63, 64, 65, 255, 256, 257, 287, 288, 289, 511, 512, 513, 767, 768, 1023, 1024,
+                      1025, 1279, 1280, 2047, 2048, 2049, 3000, 5000])
+    out = np.empty(n + 6000, np.uint8)
+    pos = 0
+    while pos < n:
+        ins = int(r.choice(edges)) if r.random() < 0.5 else int(r.integers(0, 12))
+        out[pos: pos + ins] = r.integers(0, 256, ins, dtype=np.uint8)
+        pos += ins
+        if pos == 0:
+            continue
+        cpy = int(r.choice(edges)) if r.random() < 0.4 else int(r.integers(2, 40))
+        dist = int(r.choice([1, 2, 3, 7, 64, 300, 2047, 2048, 2049, 5000, 40000])) if r.random() < 0.7 else int(r.integers(1, pos + 1))
+        dist = min(dist, pos)
+        out[pos: pos + cpy] = np.resize(out[pos - dist: pos], cpy)   # byte-serial copy: an overlap replicates its pattern
+        pos += cpy
+    return out[:n].copy()
+
+
+@functools.lru_cache(maxsize=1)
 def corner_cases() -> dict:
     r = _rng(0xC0FFEE)
     c = {}
@@ -78,6 +104,8 @@ def corner_cases() -> dict:
         o = int(rr.integers(0, 4000))
         parts += [rr.integers(0, 256, int(rr.integers(1, 6)), dtype=np.uint8), base[o: o + int(rr.integers(1100, 4800))]]
     c["small_inserts_big_copies"] = (np.concatenate(parts), {})
+    for sd in (1, 2, 3):
+        c[f"run_structure_fuzz{sd}"] = (run_structure_fuzz(140000, 0xF00 + sd), {})
     c["no_ring_codes"] = (datagen.text_like(80000, seed=30), dict(use_ring_codes=0))
     c["greedy_short_chain"] = (datagen.text_like(80000, seed=31), dict(lazy=0, max_chain=1))
     return c
