@@ -2,7 +2,7 @@
 //
 // Replaces, for the decode path only:
 //   src/decoder/BrotliGCompute.hlsl (CSMain :1753-1881: persistent waves pulling pages with atomics)
-//       -> bgx_decode_pages_kernel: persistent one-warp CTAs, one atomic page counter over ALL streams
+//       -> bgx_decode_pages_kernel: persistent two-warp CTAs (producer + consumer per page), one atomic page counter over ALL streams
 //   sample/BrotligGPUDecoder.cpp (DecodeGPU :260-748: upload, Dispatch, readback, timestamp queries)
 //       -> bgx_decode_host / bgx_decode_batch_host / bgx_plan_*: CUDA stream + events
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a (see brotli_g_sdk_b200/build.py).
@@ -271,7 +271,7 @@ int bgx_create(bgx_context** out, int device) {
     delete ctx;
     return bgx::kErrGeneric;
   }
-  // one-warp CTAs, as many as the shared-memory arena allows per SM
+  // two-warp CTAs, as many as registers and the shared-memory arena allow per SM (16)
   cudaFuncSetAttribute(bgx_decode_pages_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   int per_sm = 0;
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bgx_decode_pages_kernel, kPageThreads, 0);
