@@ -94,26 +94,30 @@ __global__ void __launch_bounds__(kPageThreads, BGX_CTAS_PER_SM) bgx_decode_page
     const uint8_t* in = s.pages + e.in_off;
     uint8_t* out = s.dst + (size_t)(page - s.page_begin) * s.page_size;
     uint32_t status = 0;
-    if (e.in_size == e.out_size) {
+    // a corrupt page table must not send any access outside the stream buffer (raw pages included), and the
+    // bit readers need their page on a 4-byte boundary (the encoder pads pages to 4 bytes)
+    const size_t avail = (size_t)(s.src_end - s.pages);
+    const bool in_bounds = (size_t)e.in_off <= avail && (size_t)e.in_size <= avail - (size_t)e.in_off;
+    if (!in_bounds) {
+      status = bgxk::kPageErrTable;
+    } else if (e.in_size == e.out_size) {
       bgxk::copy_page_cta(out, in, e.out_size);
+    } else if (e.in_size < 8u || (e.in_off & 3u) != 0u) {
+      status = bgxk::kPageErrTable;
     } else {
       bgxk::PageJob job;
       job.in = in;
       job.in_size = e.in_size;
-      const size_t room = (size_t)(s.src_end - in);
+      const size_t room = avail - (size_t)e.in_off;
       job.in_limit = room > 0xfffffff0u ? 0xfffffff0u : (uint32_t)room;
       job.out = out;
       job.out_size = e.out_size;
       job.allow_delta = s.allow_delta;
-      if (e.in_size < 8u || in + e.in_size > s.src_end) {
-        status = bgxk::kPageErrTable;
-      } else {
-        const bgxk::PageResult r = bgxk::decode_page_cta(job, &sm);
-        status = r.status;
-        if (!status && r.is_delta) {
-          if (tid >= 32) bgxk::delta_decode_warp(out, e.out_off, e.out_size, s.planes);   // the consumer warp wrote the page
-          status |= 0x40000000u;   // informational: page was delta coded
-        }
+      const bgxk::PageResult r = bgxk::decode_page_cta(job, &sm);
+      status = r.status;
+      if (!status && r.is_delta) {
+        if (tid >= 32) bgxk::delta_decode_warp(out, e.out_off, e.out_size, s.planes);   // the consumer warp wrote the page
+        status |= 0x40000000u;   // informational: page was delta coded
       }
     }
     if (tid == 0) {

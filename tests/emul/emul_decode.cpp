@@ -52,13 +52,21 @@ int emul_decode_stream(const uint8_t* src, uint32_t src_size, uint8_t* dst, uint
   for (uint32_t p = 0; p < si.num_pages; ++p) {
     const bgx::PageExtent e = bgx::page_extent(si, table, p);
     bgxk::PageResult res{0, 0};
-    if (e.in_size == e.out_size) {
+    // the same page-extent validation as bgx_decode_pages_kernel (bgx_cuda.cu)
+    const uint8_t* src_end = src + ((src_size + 15u) & ~15u);
+    const size_t avail = (size_t)(src_end - pages);
+    const bool in_bounds = (size_t)e.in_off <= avail && (size_t)e.in_size <= avail - (size_t)e.in_off;
+    if (!in_bounds) {
+      res.status = bgxk::kPageErrTable;
+    } else if (e.in_size == e.out_size) {
       coll += wemu::run_block(2, [&] { bgxk::copy_page_cta(dst + e.out_off, pages + e.in_off, e.out_size); });
+    } else if (e.in_size < 8u || (e.in_off & 3u) != 0u) {
+      res.status = bgxk::kPageErrTable;
     } else {
       bgxk::PageJob job;
       job.in = pages + e.in_off;
       job.in_size = e.in_size;
-      job.in_limit = (uint32_t)((src + src_size + 16) - (pages + e.in_off));
+      job.in_limit = (uint32_t)(avail - (size_t)e.in_off);
       job.out = dst + e.out_off;
       job.out_size = e.out_size;
       job.allow_delta = si.preconditioned;

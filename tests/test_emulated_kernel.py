@@ -47,9 +47,13 @@ def test_emulated_kernel_rejects_garbage_without_writing_out_of_bounds(sdk, emul
     data = np.tile(rng.integers(0, 256, 997, dtype=np.uint8), 80)
     s = sdk.Encode(data)
     assert len(s) < len(data) // 2
-    for trial in range(12):
+    n_pages = int(s[2]) | (int(s[3]) << 8)
+    for trial in range(18):
         bad = s.copy()
-        k = int(rng.integers(20, len(bad) - 4))
+        if trial % 3 == 2:      # a corrupt page-table entry: offsets/sizes that point anywhere
+            k = 8 + 4 * int(rng.integers(0, n_pages))
+        else:                   # corrupt payload bytes
+            k = int(rng.integers(8 + 4 * n_pages, len(bad) - 4))
         bad[k: k + 4] ^= rng.integers(1, 256, 4, dtype=np.uint8)
         try:
             emulator.decode(bad, expect_rc=0)
