@@ -519,41 +519,13 @@ int bgx_decode_batch_host(bgx_context* ctx, uint32_t n, const uint8_t* const* in
 
   // Three-stage pipeline: upload (s_in) -> kernels (ctx->stream) -> download (s_out); uploads and downloads run
   // concurrently on the two PCIe directions (the reference host serialises upload -> dispatch -> readback,
-  // BrotligGPUDecoder.cpp:633-727). The unit of the pipeline is a SEGMENT: a whole stream, or -- for streams that
-  // are large against the batch -- a range of its pages (pages are independent and contiguous in the stream, so a
-  // range needs the stream's bytes up to the end of its last page and produces a contiguous slice of the output).
-  // A single 64 MiB stream therefore overlaps its own upload, decode and download too.
-  struct Segment {
-    uint32_t stream, page_begin, page_count;   // page_count 0 = the whole stream
-    size_t up0, up1;                           // stream bytes [up0, up1) to upload before this segment can run
-    size_t dn0, dn1;                           // output bytes [dn0, dn1) it produces
-  };
+  // BrotligGPUDecoder.cpp:633-727). The unit of the pipeline is a segment (host_plan.h): a whole stream, or a page
+  // range of a stream that is large against the batch, so a single 64 MiB stream overlaps its own three phases too.
+  using Segment = bgx::HostSegment;
   const size_t total = in_total + out_total;
   const size_t target = std::max<size_t>(48u << 20, total / 12);   // (finer units measured no faster: PCIe is the bound)
   std::vector<Segment> seg;
-  for (uint32_t i = 0; i < n; ++i) {
-    const StreamInfo& si = info[i];
-    const size_t bytes = (size_t)input_sizes[i] + si.uncompressed_size;
-    const size_t table_end = (size_t)si.header_bytes + 4ull * si.num_pages;
-    uint32_t parts = (uint32_t)std::min<size_t>((bytes + target - 1) / target, si.num_pages);
-    if (si.preconditioned || parts < 2 || table_end > input_sizes[i]) {   // (a truncated table is reported by the plan)
-      seg.push_back(Segment{i, 0, 0, 0, input_sizes[i], 0, si.uncompressed_size});
-      continue;
-    }
-    const uint32_t per = (si.num_pages + parts - 1) / parts;
-    size_t up_prev = 0;
-    for (uint32_t pb = 0; pb < si.num_pages; pb += per) {
-      const uint32_t pc = std::min(per, si.num_pages - pb);
-      const bool last = pb + pc == si.num_pages;
-      // end of the range's last page inside the stream: page table entry pb + pc (offset from the end of the table)
-      size_t up1 = last ? (size_t)input_sizes[i] : table_end + bgx::load_le32(inputs[i] + si.header_bytes + 4ull * (pb + pc));
-      up1 = std::min<size_t>(std::max(up1, std::max(up_prev, table_end)), input_sizes[i]);   // corrupt tables stay in bounds
-      const size_t dn0 = (size_t)pb * si.page_size;
-      const size_t dn1 = last ? (size_t)si.uncompressed_size : (size_t)(pb + pc) * si.page_size;
-      seg.push_back(Segment{i, pb, pc, up_prev, up1, dn0, dn1});
-      up_prev = up1;
-    }
-  }
+  for (uint32_t i = 0; i < n; ++i) bgx::plan_stream_segments(i, inputs[i], input_sizes[i], info[i], target, seg);
   const uint32_t ns = (uint32_t)seg.size();
   std::vector<bgx_stream> st(ns);
   for (uint32_t k = 0; k < ns; ++k) {

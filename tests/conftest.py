@@ -104,6 +104,15 @@ class Emulator:
             _run(["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-w", "-I" + d] + extra + [deps[0], "-o", so])
         self.lib = ctypes.CDLL(so)
         self.lib.emul_decode_stream.restype = ctypes.c_int
+        self.lib.emul_plan_segments.restype = ctypes.c_int
+
+    def plan_segments(self, stream: np.ndarray, target: int):
+        """host_plan.h plan_stream_segments for one stream: list of (page_begin, page_count, up0, up1, dn0, dn1)"""
+        s = np.ascontiguousarray(stream, dtype=np.uint8)
+        out = (ctypes.c_uint64 * (7 * 4096))()
+        n = self.lib.emul_plan_segments(ctypes.c_void_p(s.ctypes.data), ctypes.c_uint32(len(s)), ctypes.c_uint64(target), out, 4096)
+        assert n >= 0
+        return [tuple(int(out[7 * k + j]) for j in range(1, 7)) for k in range(n)]
 
     def decode(self, stream: np.ndarray, expect_rc: int = 0, dst_offset: int = 0):
         s = np.ascontiguousarray(stream, dtype=np.uint8)

@@ -100,4 +100,20 @@ void emul_stats(uint64_t* out14, int reset) {
 }
 #endif
 uint32_t emul_warp_smem_bytes() { return (uint32_t)sizeof(bgxk::WarpSmem); }
+
+// The host-pointer pipeline's segment planner (host_plan.h), for the CPU unit test. Writes 7 numbers per segment
+// (stream, page_begin, page_count, up0, up1, dn0, dn1); returns the number of segments or -1.
+int emul_plan_segments(const uint8_t* input, uint32_t input_size, uint64_t target, uint64_t* out7, uint32_t max_segments) {
+  bgx::StreamInfo si;
+  if (input_size < bgx::kStreamHeaderBytes || bgx::parse_stream_header(input, &si)) return -1;
+  std::vector<bgx::HostSegment> seg;
+  bgx::plan_stream_segments(0, input, input_size, si, (size_t)target, seg);
+  if (seg.size() > max_segments) return -1;
+  for (size_t k = 0; k < seg.size(); ++k) {
+    const bgx::HostSegment& g = seg[k];
+    const uint64_t v[7] = {g.stream, g.page_begin, g.page_count, g.up0, g.up1, g.dn0, g.dn1};
+    for (int j = 0; j < 7; ++j) out7[7 * k + j] = v[j];
+  }
+  return (int)seg.size();
+}
 }
