@@ -40,7 +40,9 @@ int bgx_decode_host(bgx_context* ctx, uint32_t input_size, const uint8_t* input,
 
 /* Batch form of the above: n independent streams decoded by ONE launch sequence (the reference's shader
  * consumes a list of streams per dispatch: src/decoder/BrotliGCompute.hlsl:1757-1775). Host pointers.
- * output_sizes[i]: in = capacity, out = uncompressed size. Copies are pipelined with the kernels. */
+ * output_sizes[i]: in = capacity, out = uncompressed size. Uploads, kernels and downloads are pipelined over groups
+ * of streams and, for streams that are large against the batch, over page ranges of a stream (pinned host
+ * buffers make the copies asynchronous; pageable ones work, serialised by the driver). */
 int bgx_decode_batch_host(bgx_context* ctx, uint32_t n, const uint8_t* const* inputs, const uint32_t* input_sizes,
                           uint8_t* const* outputs, uint32_t* output_sizes, double* kernel_ms);
 
