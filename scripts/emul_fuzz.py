@@ -20,6 +20,7 @@ for name in names:
     d,kw=cc[name]; d=d[:200000]
     s=b.Encode(d,**kw)
     n=int(s[2])|int(s[3])<<8
+    if len(s) < 8+4*n+24: continue      # too small to corrupt meaningfully
     for t in range(trials):
         bad=s.copy()
         mode=int(rng.integers(0,3))
