@@ -846,6 +846,35 @@ BGX_DEV void producer_warp(const PageJob& job, WarpSmem* sm) {
       const uint32_t src_lane = from_carry ? 0u : (uint32_t)(31 - __clz((int)b));
       const uint32_t cslot = slot - (from_carry ? npush_below : 0u);
       const uint32_t carry_val = cslot == 0 ? r0 : cslot == 1 ? r1 : cslot == 2 ? r2 : r3;
+#ifdef BGX_RING_PJ
+      // EXPERIMENT (off by default, not yet measured on the GPU): pointer jumping instead of relaxation. Every
+      // unresolved command holds (source lane, accumulated offset); a step either picks up the source's final
+      // value or adopts the source's own source, so a chain of length n resolves in ceil(log2 n) + 1 steps instead
+      // of n (record-like data averages 5.6 relaxation steps per round).
+      if (unresolved && from_carry) {
+        dist = (uint32_t)((int32_t)carry_val + delta);
+        unresolved = false;
+      }
+      uint32_t ptr = src_lane;
+      int32_t off = delta;
+      uint32_t pend = __ballot_sync(kFull, unresolved);
+      while (pend) {
+        BGX_STAT(emu_stats().ring_iters++);
+        const uint32_t t_dist = __shfl_sync(kFull, dist, ptr);
+        const uint32_t t_ptr = __shfl_sync(kFull, ptr, ptr);
+        const int32_t t_off = __shfl_sync(kFull, off, ptr);
+        if (unresolved) {
+          if (!((pend >> ptr) & 1u)) {            // the source is final: so am I
+            dist = (uint32_t)((int32_t)t_dist + off);
+            unresolved = false;
+          } else {                                // hop over the source
+            off += t_off;
+            ptr = t_ptr;
+          }
+        }
+        pend = __ballot_sync(kFull, unresolved);
+      }
+#else
       uint32_t resolved = __ballot_sync(kFull, !unresolved);
       while (resolved != kFull) {
         BGX_STAT(emu_stats().ring_iters++);
@@ -857,6 +886,7 @@ BGX_DEV void producer_warp(const PageJob& job, WarpSmem* sm) {
         }
         resolved = __ballot_sync(kFull, !unresolved);
       }
+#endif
       }
       if (push) {   // new carried ring = four most recent pushers of this round, then the old ring
         uint32_t pb = push;
