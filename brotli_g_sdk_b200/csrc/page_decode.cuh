@@ -77,7 +77,10 @@ constexpr uint32_t kLitQ = 512;       // literal ring bytes (power of two): two 
 #endif
 constexpr uint32_t kRing = BGX_RING;      // output ring bytes (power of two, >= kFlushChunk + kRoundMax)
 constexpr uint32_t kRoundMax = 1024;  // largest round (bytes produced) the ring path accepts
-constexpr uint32_t kSplitLits = 256;  // literals per virtual round when a long round is split (two fit the literal ring)
+#ifndef BGX_SPLIT_LITS
+#define BGX_SPLIT_LITS 256
+#endif
+constexpr uint32_t kSplitLits = BGX_SPLIT_LITS;  // literals per virtual round when a long round is split (two fit the literal ring; <= kLitQ - 64)
 constexpr uint32_t kFlushChunk = 512; // 32 lanes x 16 B
 constexpr uint32_t kCoopLen = 32;     // inserts/copies at least this long are done by the whole warp
 constexpr uint16_t kLongCode = 0xffffu;  // primary-LUT marker: code longer than the LUT index
