@@ -1067,6 +1067,46 @@ BGX_DEV void consumer_warp(const PageJob& job, WarpSmem* sm) {
     //      literal index turns "which command owns literal t" into one popc.
     uint32_t* tab = sm->scratch;                       // [32] (o_ins - first literal index)
     const saddr_t ring_a = saddr(sm->ring), litq_a = saddr(sm->litq), tab_a = saddr(sm->scratch);
+#ifdef BGX_INS_PIECES
+    // EXPERIMENT (off by default, not yet measured on the GPU): literal-heavy rounds (>= BGX_INS_PIECES literals, e.g.
+    // the 256-literal virtual rounds of noisy data) place their literals as 4-byte pieces, like the ready copies:
+    // the literals of one command are contiguous in the literal ring and in the output.
+    if (round_ins >= (uint32_t)(BGX_INS_PIECES)) {
+      const uint32_t np = (ins + 3u) >> 2;
+      const uint32_t E = warp_incl_scan(np, lane);
+      const uint32_t T = __shfl_sync(kFull, E, 31);
+      const uint32_t S = E - np;
+      const uint32_t has = __ballot_sync(kFull, ins != 0);
+      // entry: (dst - 4 * first piece index, literal index of the first literal - 4 * first piece index | (end - that) << 17)
+      uint2* tabp = reinterpret_cast<uint2*>(sm->scratch + 32);
+      if (ins) tabp[__popc(has & lt_mask)] = make_uint2(o_ins - 4u * S, ((lit_head + lq - 4u * S) & 0x1ffffu) | ((4u * S + ins) << 17));
+      __syncwarp();
+      const uint32_t pcidx = S >> 5;
+      const uint32_t pcbit = ins ? (1u << (S & 31u)) : 0u;
+      const uint32_t plast = __popc(has) - 1u;
+      uint32_t before = 0;
+#pragma unroll 1
+      for (uint32_t c = 0, t = lane; 32u * c < T; ++c, t += 32u) {
+        const uint32_t M = __reduce_or_sync(kFull, pcidx == c ? pcbit : 0u);
+        uint32_t ord = before + __popc(M & le_mask) - 1u;
+        before += __popc(M);
+        ord = ord < plast ? ord : plast;
+        const uint2 e = lds_u32x2(tab_a + 128u + 8u * ord);
+        const uint32_t d = e.x + 4u * t;
+        const uint32_t li = (e.y & 0x1ffffu) + 4u * t;                 // literal index (mod 2^17; the ring is 512)
+        int32_t rem = (int32_t)((e.y >> 17) - 4u * t);
+        if (t >= T) rem = 0;
+        const uint32_t a = li & (kLitQ - 4u);
+        const uint32_t lo = lds_u32(litq_a + a);
+        const uint32_t hi = lds_u32(litq_a + ((a + 4u) & (kLitQ - 1)));
+        const uint32_t v = __funnelshift_r(lo, hi, (li & 3u) * 8u);
+        if (rem > 0) sts_u8(ring_a + (d & (kRing - 1)), v);
+        if (rem > 1) sts_u8(ring_a + ((d + 1u) & (kRing - 1)), v >> 8);
+        if (rem > 2) sts_u8(ring_a + ((d + 2u) & (kRing - 1)), v >> 16);
+        if (rem > 3) sts_u8(ring_a + ((d + 3u) & (kRing - 1)), v >> 24);
+      }
+    } else
+#endif
     {
       const uint32_t has = __ballot_sync(kFull, ins != 0);
       if (ins) tab[__popc(has & lt_mask)] = o_ins - lq;
