@@ -71,7 +71,10 @@ constexpr int kCmdLutBits = 9;
 #endif
 constexpr int kLitLutBits = BGX_LITBITS;
 constexpr int kDistLutBits = 9;
-constexpr uint32_t kLitQ = 512;       // literal ring bytes (power of two): two rounds' literals (producer runs one ahead)
+#ifndef BGX_LITQ
+#define BGX_LITQ 512
+#endif
+constexpr uint32_t kLitQ = BGX_LITQ;  // literal ring bytes (power of two): the literals of the rounds in flight
 #ifndef BGX_RING
 #define BGX_RING 2048
 #endif
@@ -80,7 +83,8 @@ constexpr uint32_t kRoundMax = 1024;  // largest round (bytes produced) the ring
 #ifndef BGX_SPLIT_LITS
 #define BGX_SPLIT_LITS 256
 #endif
-constexpr uint32_t kSplitLits = BGX_SPLIT_LITS;  // literals per virtual round when a long round is split (two fit the literal ring; <= kLitQ - 64)
+constexpr uint32_t kSplitLits = BGX_SPLIT_LITS;  // literals per virtual round when a long round is split (two fit the literal ring)
+static_assert((kLitQ & (kLitQ - 1)) == 0 && kSplitLits + 128 <= kLitQ, "a virtual round's literals (+ rows decoded ahead) must fit the literal ring");
 constexpr uint32_t kFlushChunk = 512; // 32 lanes x 16 B
 constexpr uint32_t kCoopLen = 32;     // inserts/copies at least this long are done by the whole warp
 constexpr uint16_t kLongCode = 0xffffu;  // primary-LUT marker: code longer than the LUT index
