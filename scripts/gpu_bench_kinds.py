@@ -1,5 +1,6 @@
 """Device-resident decode throughput of several payload kinds in one process (kernel experiments).
 usage: gpu_bench_kinds.py [MiB per stream=16] [copies=32] [kinds=text,binary,mixed,lowent]
+       ("texture" is a 16 MiB BC3 texture with swizzle + delta pre-conditioning, whatever the size argument says)
 Prints one line: <lib> kind=GB/s ... (median of 5 launches, outputs verified against the source)."""
 import os, sys
 import numpy as np
@@ -15,8 +16,14 @@ gen = {"text": datagen.text_like, "lowent": datagen.low_entropy, "random": datag
 dec = b.BrotligDecoder(0)
 res = []
 for kind in kinds:
-    data = gen[kind](mib << 20, seed=21)
-    s = b.Encode(data)
+    if kind == "texture":
+        from brotli_g_sdk_b200.encoder import DataconditionParams
+        data = datagen.bc_texture(1024, 1024, 3, seed=21)
+        s = b.Encode(data, dcParams=DataconditionParams(precondition=True, swizzle=True, delta_encode=True, format=3,
+                                                         width_blocks=1024, height_blocks=1024))
+    else:
+        data = gen[kind](mib << 20, seed=21)
+        s = b.Encode(data)
     sd, keep = [], []
     for c in range(copies):
         t_in = torch.empty(len(s) + 64, dtype=torch.uint8, device="cuda"); t_in[: len(s)] = torch.from_numpy(s).cuda()
