@@ -97,6 +97,7 @@ def corner_cases() -> dict:
     for i in range(90):
         parts += [rr.integers(0, 256, int(rr.integers(300, 1500)), dtype=np.uint8), key[: int(rr.integers(8, 64))]]
     c["big_inserts_small_copies"] = (np.concatenate(parts), {})
+    parts_big = parts
     # ... and the mirror image: a few literals, then kilobytes copied from far back (copies longer than a round takes)
     base = rr.integers(0, 256, 9000, dtype=np.uint8)
     parts = [base]
@@ -106,6 +107,8 @@ def corner_cases() -> dict:
     c["small_inserts_big_copies"] = (np.concatenate(parts), {})
     for sd in (1, 2, 3):
         c[f"run_structure_fuzz{sd}"] = (run_structure_fuzz(140000, 0xF00 + sd), {})
+    c["run_structure_fuzz_small"] = (run_structure_fuzz(45000, 0xF10), {})      # small enough for a golden fixture
+    c["big_inserts_small"] = (np.concatenate(parts_big[:40]), {})
     c["no_ring_codes"] = (datagen.text_like(80000, seed=30), dict(use_ring_codes=0))
     c["greedy_short_chain"] = (datagen.text_like(80000, seed=31), dict(lazy=0, max_chain=1))
     return c
