@@ -31,6 +31,7 @@
 // The file is also compiled by g++ against tests/emul/warp_emul.h (BGX_EMULATED) so that the very
 // same code can be exercised on the CPU-only development box. That emulator is test infrastructure.
 #pragma once
+#include <stddef.h>
 #include <stdint.h>
 
 #include <type_traits>
@@ -107,13 +108,14 @@ struct HuffAux {
 #define BGX_Q 4
 #endif
 constexpr uint32_t kQ = BGX_Q;   // rounds in flight between the producer and the consumer warp (power of two)
-struct RoundBuf {            // one round of <= 32 commands, producer -> consumer (only rounds of <= kRoundMax bytes;
-  uint32_t dx[32];           //   resolved match distance              long-run rounds stay in the producer's registers)
-  uint32_t pk[32];           //   inclusive prefix sums over the commands: bytes produced | literals consumed << 16
-};
-struct PageCtl {             // hand-over state of the two warps of a page (ordered by the named barriers)
+struct RoundBuf {            // one round of <= 32 commands, producer -> consumer (a round never produces more than
+  uint2 cmd[32];             //   kRoundMax bytes: longer ones travel as several virtual rounds)
+};                           //   .x resolved match distance
+                             //   .y inclusive prefix sums over the commands: bytes produced (bits 0..11) | literals consumed
+                             //      (bits 16..27), plus the round's flags (kPkLast / kPkAbort, the same in every lane)
+enum : uint32_t { kPkLast = 1u << 12, kPkAbort = 1u << 13, kPkSums = 0x0fff0fffu };
+struct PageCtl {             // hand-over state of the two warps of a page
   uint32_t err, is_delta;
-  uint32_t rflags[kQ];           // per RoundBuf: kFlagLast | kFlagAbort
   uint32_t phead[kQ];            // producer only: literal head at the start of the round in that slot
 };
 
@@ -144,22 +146,41 @@ struct WarpSmem {
 #ifdef BGX_EMULATED
 typedef uintptr_t saddr_t;
 BGX_DEV saddr_t saddr(const void* p) { return reinterpret_cast<uintptr_t>(p); }
+BGX_DEV saddr_t saddr_pinned(const void* p) { return reinterpret_cast<uintptr_t>(p); }
 BGX_DEV uint32_t lds_u8(saddr_t a) { return *reinterpret_cast<const uint8_t*>(a); }
 BGX_DEV void sts_u8(saddr_t a, uint32_t v) { *reinterpret_cast<uint8_t*>(a) = (uint8_t)v; }
 BGX_DEV uint32_t lds_u32(saddr_t a) { return *reinterpret_cast<const uint32_t*>(a); }
 BGX_DEV uint2 lds_u32x2(saddr_t a) { return *reinterpret_cast<const uint2*>(a); }
+BGX_DEV void sts_u32(saddr_t a, uint32_t v) { *reinterpret_cast<uint32_t*>(a) = v; }
+BGX_DEV void sts_u32x2(saddr_t a, uint32_t x, uint32_t y) { uint32_t* p = reinterpret_cast<uint32_t*>(a); p[0] = x; p[1] = y; }
 BGX_DEV uint32_t ldg_u8(const uint8_t* p) { return *p; }
 BGX_DEV uint32_t ldg_u32(const uint32_t* p) { return *p; }
 #else
 typedef uint32_t saddr_t;
 BGX_DEV saddr_t saddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// the same, opaque to the optimiser: it keeps the address in a register instead of re-deriving it (S2R CgaCtaId +
+// LEA) next to every access of a hot loop
+BGX_DEV saddr_t saddr_pinned(const void* p) { uint32_t a = (uint32_t)__cvta_generic_to_shared(p); asm volatile("" : "+r"(a)); return a; }
 BGX_DEV uint32_t lds_u8(saddr_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 BGX_DEV void sts_u8(saddr_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 BGX_DEV uint32_t lds_u32(saddr_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 BGX_DEV uint2 lds_u32x2(saddr_t a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
+BGX_DEV void sts_u32(saddr_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+BGX_DEV void sts_u32x2(saddr_t a, uint32_t x, uint32_t y) { asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory"); }
 BGX_DEV uint32_t ldg_u8(const uint8_t* p) { uint32_t v; asm volatile("ld.global.u8 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
 BGX_DEV uint32_t ldg_u32(const uint32_t* p) { uint32_t v; asm volatile("ld.global.u32 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
 #endif
+
+// keeps a loop-invariant value in its register (the optimiser otherwise re-derives cheap ones inside hot loops)
+BGX_DEV uint32_t pinned(uint32_t v) {
+#ifndef BGX_EMULATED
+  asm volatile("" : "+r"(v));
+#endif
+  return v;
+}
+// byte p of the output ring / literal index g of the literal ring
+BGX_DEV saddr_t ring_at(saddr_t ring_a, uint32_t p) { return ring_a + (p & (kRing - 1u)); }
+BGX_DEV saddr_t litq_at(saddr_t litq_a, uint32_t g) { return litq_a + (g & (kLitQ - 1u)); }
 
 // ---------------------------------------------------------------------------------------------
 // Input staging + bit reader. Every lane reads its own sub-stream strictly sequentially, so the
@@ -593,7 +614,6 @@ BGX_DEV void decode_literals(WarpSmem* sm, BitRd& rd, PageIn& in, uint32_t tail,
 // A round with long runs (more than kRoundMax bytes, or more literals than the literal ring holds) travels as a
 // sequence of "virtual" rounds that each fit (see the producer), so the consumer only ever sees one kind of round.
 // The mbarriers are re-initialised at the start of every page (the CTA is persistent and decodes many pages).
-enum : uint32_t { kFlagLast = 1u, kFlagAbort = 4u };
 
 // full[] / empty[] are mbarriers in shared memory (no per-SM resource besides 8 bytes each;
 // named bar.sync barriers would cap the resident CTAs per SM): one elected lane arrives (release) after a
@@ -708,30 +728,28 @@ BGX_DEV void producer_warp(const PageJob& job, WarpSmem* sm) {
   if (!terr) terr = load_table<kDistLutBits>(sm, rd, in, bgx::kNumDistSymbols, sm->lut_dist, sm->aux[1], sm->sorted_dist, lane);
   if (!terr) terr = load_table<kLitLutBits>(sm, rd, in, bgx::kNumLitSymbols, sm->lut_lit, sm->aux[2], sm->sorted_lit, lane);
   __syncwarp();
-  if (terr && lane == 0) ctl->err = terr;
-  __syncwarp();
 
   const saddr_t full_a = saddr(sm->mbar), empty_a = full_a + 8u * kQ;
   uint32_t rnd = 0;            // rounds published so far
   uint32_t synced = 0;         // empty[] phases taken so far: rounds < synced are known to be consumed
   uint32_t lit_tail = 0;       // literals decoded so far
   uint32_t lit_head_p = 0;     // literals that the rounds published so far consume
-  uint32_t r0 = 4, r1 = 11, r2 = 15, r3 = 16;   // distance ring (PageDecoder.cpp:150-153)
+  uint32_t ringv = (0x100f0b04u >> (8u * (lane & 3u))) & 0xffu;   // distance ring {4, 11, 15, 16} (PageDecoder.cpp:150-153): lane l keeps entry l & 3
   bool pdone = false;
   uint32_t pos_p = 0;          // bytes the rounds published so far produce
-  // waits until slot rnd % kQ is free; false when the page is being aborted (the abort round is then published)
-  auto acquire_slot = [&]() -> bool {
+  // ends the page with an error: the slot of round `rnd` (free: every caller has acquired it) carries the abort flag
+  auto publish_abort = [&](uint32_t err) {
     const uint32_t q = rnd & (kQ - 1u);
+    if (err && lane == 0) ctl->err = err;
+    sm->rb[q].cmd[lane] = make_uint2(0u, kPkAbort);
+    warp_arrive(full_a + 8u * q, lane);
+  };
+  // waits until slot rnd % kQ is free
+  auto acquire_slot = [&]() {
     while (synced + kQ <= rnd) {   // the slot still holds round rnd - kQ: wait until the consumer is done with it
       mbar_wait(empty_a + 8u * (synced & (kQ - 1u)), (synced / kQ) & 1u);
       ++synced;
     }
-    if (ld_volatile_u32(&ctl->err)) {   // a table error, or the consumer rejected a round: tell it to stop
-      if (lane == 0) ctl->rflags[q] = kFlagAbort;
-      warp_arrive(full_a + 8u * q, lane);
-      return false;
-    }
-    return true;
   };
   // the literal ring must hold `newlits` more literals next to those of every round the consumer may still be
   // working on (rounds >= synced): takes more empty[] phases while that helps; false if they cannot fit at all
@@ -748,80 +766,79 @@ BGX_DEV void producer_warp(const PageJob& job, WarpSmem* sm) {
   };
   auto publish = [&](uint32_t dxv, uint32_t pkv, uint32_t flags) {
     const uint32_t q = rnd & (kQ - 1u);
-    RoundBuf* rb = &sm->rb[q];
-    rb->dx[lane] = dxv;            // final distance
-    rb->pk[lane] = pkv;            // inclusive sums: output | literals << 16
-    if (lane == 0) ctl->rflags[q] = flags;
+    sm->rb[q].cmd[lane] = make_uint2(dxv, pkv | flags);   // final distance; inclusive sums: output | literals << 16
     warp_arrive(full_a + 8u * q, lane);
     ++rnd;
   };
+  if (terr) {   // a malformed prefix-code description: the page ends here
+    publish_abort(terr);
+    return;
+  }
+  const uint32_t postfix_mask = (1u << npostfix) - 1u;
   for (;;) {
-    if (!acquire_slot()) break;
-    const uint32_t q = rnd & (kQ - 1u);
+    acquire_slot();
     br_topup1(rd, in);
-    // ---- one command per lane, speculatively (lanes after the sentinel roll back)
-    BitRd r = rd;
+    // ---- one command per lane, speculatively: the lanes behind the sentinel consume nothing. Straight-line code
+    //      with two window refills (after the insert&copy part and after the distance part); only 24-bit extra
+    //      fields branch off.
+    const uint32_t pk = br_peek(rd);
     uint32_t len;
-    const uint32_t pk = br_peek(r);
-    uint32_t sym = huff_decode<kCmdLutBits>(sm->lut_cmd, sm->aux[0], sm->sorted_cmd, bgx::kNumCmdSymbols, pk, len);
+    const uint32_t sym = huff_decode<kCmdLutBits>(sm->lut_cmd, sm->aux[0], sm->sorted_cmd, bgx::kNumCmdSymbols, pk, len);
     const uint32_t sent = __ballot_sync(kFull, sym == (uint32_t)bgx::kCmdSentinel);
     const uint32_t n = sent ? (uint32_t)(__ffs((int)sent) - 1) : 32u;   // commands in this round
     pdone = sent != 0;
-    uint32_t ins = 0, cpy = 0, dx = 0;   // dx: explicit distance, or 0x80000000 | short code 0..15
-    if (lane < n) {
-      uint32_t ic, cc = 0;
-      bool has_copy = false;
-      if (sym < (uint32_t)bgx::kCmdSentinel) {
-        ic = bgx::icp_insert_code(sym);
-        cc = bgx::icp_copy_code(sym);
-        has_copy = true;
-      } else {
-        ic = sym - (uint32_t)bgx::kCmdSentinel;      // insert-only (PageDecoder.cpp:308-317)
-        if (ic > 23u) ic = 23u;
-      }
-      const uint32_t ei = sm->lenlut[ic];
-      const uint32_t ec = has_copy ? sm->lenlut[24 + cc] : 0u;
-      const uint32_t nbi = ei >> 16, nbc = ec >> 16;
-      if (len + nbi + nbc <= 32u) {   // symbol + both extra-bit fields out of the one 32-bit peek
-        ins = (ei & 0xffffu) + (shr32(pk, len) & low_mask(nbi));
-        cpy = (ec & 0xffffu) + (shr32(pk, len + nbi) & low_mask(nbc));
-        br_skip(r, in, len + nbi + nbc);
-      } else {                        // 24-bit extras: field by field
-        br_skip(r, in, len);
-        ins = (ei & 0xffffu) + br_read(r, in, nbi);
-        cpy = (ec & 0xffffu) + br_read(r, in, nbc);
-      }
-      if (has_copy) {
+    const bool act = lane < n;
+    const bool has_copy = sym < (uint32_t)bgx::kCmdSentinel;            // else insert-only (PageDecoder.cpp:308-317)
+    uint32_t ic = sym - (uint32_t)bgx::kCmdSentinel;
+    ic = has_copy ? bgx::icp_insert_code(sym) : (ic > 23u ? 23u : ic);
+    const uint32_t ei = sm->lenlut[ic];
+    const uint32_t ec = has_copy ? sm->lenlut[24u + bgx::icp_copy_code(sym)] : 0u;
+    const uint32_t nbi = ei >> 16, nbc = ec >> 16;
+    uint32_t adv = len + nbi + nbc;
+    uint32_t ins = ei & 0xffffu, cpy = ec & 0xffffu;
+    if (act && adv > 32u) {           // 24-bit extras: field by field
+      br_skip(rd, in, len);
+      ins += br_read(rd, in, nbi);
+      cpy += br_read(rd, in, nbc);
+      adv = 0;
+    } else {                          // symbol + both extra-bit fields out of the one 32-bit peek
+      ins += shr32(pk, len) & low_mask(nbi);
+      cpy += shr32(pk, len + nbi) & low_mask(nbc);
+    }
+    if (!act) {
+      ins = 0;
+      cpy = 0;
+      adv = lane == n ? len : 0u;     // the sentinel's code bits are consumed; its lane then continues with literals
+    }
+    br_skip(rd, in, adv);
+    uint32_t dx = 0;                  // explicit distance, or 0x80000000 | short code 0..15
+    {
+      uint32_t adv2 = 0;
+      if (cpy) {
         dx = 0x80000000u;             // implicit "last distance" (symbol < 128, PageDecoder.cpp:305)
         if (sym >= 128u) {
-          const uint32_t pk2 = br_peek(r);
-          const uint32_t dcode = huff_decode<kDistLutBits>(sm->lut_dist, sm->aux[1], sm->sorted_dist, bgx::kNumDistSymbols, pk2, len);
-          if (dcode >= 16u + ndirect) {   // explicit distance with extra bits (PageDecoder.cpp:376-394)
-            const uint32_t v = dcode - ndirect - 16u;
-            uint32_t nb = 1u + (v >> (npostfix + 1u));
-            if (nb > 24u) nb = 24u;
-            uint32_t extra;
-            if (len + nb <= 32u) {
-              extra = shr32(pk2, len) & low_mask(nb);
-              br_skip(r, in, len + nb);
-            } else {
-              br_skip(r, in, len);
-              extra = br_read(r, in, nb);
-            }
-            const uint32_t h = v >> npostfix, lo = v & ((1u << npostfix) - 1u);
-            dx = (((((2u + (h & 1u)) << nb) - 4u + extra) << npostfix) + lo + ndirect + 1u) & 0x7fffffffu;
+          const uint32_t pk2 = br_peek(rd);
+          uint32_t len2;
+          const uint32_t dcode = huff_decode<kDistLutBits>(sm->lut_dist, sm->aux[1], sm->sorted_dist, bgx::kNumDistSymbols, pk2, len2);
+          const bool expl = dcode >= 16u + ndirect;                     // distance with extra bits (PageDecoder.cpp:376-394)
+          const uint32_t v = dcode - ndirect - 16u;
+          uint32_t nb = 1u + (v >> (npostfix + 1u));
+          nb = expl ? (nb > 24u ? 24u : nb) : 0u;
+          uint32_t extra;
+          if (len2 + nb <= 32u) {
+            extra = shr32(pk2, len2) & low_mask(nb);
+            adv2 = len2 + nb;
           } else {
-            br_skip(r, in, len);
-            dx = dcode >= 16u ? dcode - 15u : (0x80000000u | dcode);   // direct codes (PageDecoder.cpp:369-373) / ring codes
+            br_skip(rd, in, len2);
+            extra = br_read(rd, in, nb);
           }
+          const uint32_t h = v >> npostfix, lo = v & postfix_mask;
+          const uint32_t dexp = (((((2u + (h & 1u)) << nb) - 4u + extra) << npostfix) + lo + ndirect + 1u) & 0x7fffffffu;
+          // direct codes (PageDecoder.cpp:369-373) / ring codes
+          dx = expl ? dexp : (dcode >= 16u ? dcode - 15u : (0x80000000u | dcode));
         }
-      } else {
-        cpy = 0;
       }
-      rd = r;
-    } else if (lane == n) {
-      br_skip(r, in, len);
-      rd = r;   // the sentinel's code bits are consumed; its lane then continues with literals
+      br_skip(rd, in, adv2);
     }
     // ---- distance ring, resolved by relaxation (PageDecoder.cpp:345-404)
     {
@@ -852,7 +869,7 @@ BGX_DEV void producer_warp(const PageJob& job, WarpSmem* sm) {
       const bool from_carry = slot >= npush_below;
       const uint32_t src_lane = from_carry ? 0u : (uint32_t)(31 - __clz((int)b));
       const uint32_t cslot = slot - (from_carry ? npush_below : 0u);
-      const uint32_t carry_val = cslot == 0 ? r0 : cslot == 1 ? r1 : cslot == 2 ? r2 : r3;
+      const uint32_t carry_val = __shfl_sync(kFull, ringv, (int)cslot);
 #ifdef BGX_RING_PJ
       // EXPERIMENT (off by default, not yet measured on the GPU): pointer jumping instead of relaxation. Every
       // unresolved command holds (source lane, accumulated offset); a step either picks up the source's final
@@ -895,47 +912,60 @@ BGX_DEV void producer_warp(const PageJob& job, WarpSmem* sm) {
       }
 #endif
       }
-      if (push) {   // new carried ring = four most recent pushers of this round, then the old ring
-        uint32_t pb = push;
-        uint32_t nr[4];
-        uint32_t old_idx = 0;
+      if (push) {   // new carried ring = the four most recent pushers of this round, then the old ring
+        // lane l keeps ring[l & 3]: it wants the (l & 3)-th most recent pusher, or -- past the pushers -- an old entry
+        const uint32_t j = lane & 3u;
+        uint32_t pbj = push;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint32_t hb = pb ? (uint32_t)(31 - __clz((int)pb)) : 0u;
-          const uint32_t v = __shfl_sync(kFull, dist, hb);
-          if (pb) { nr[k] = v; pb &= ~(1u << hb); }
-          else { nr[k] = old_idx == 0 ? r0 : old_idx == 1 ? r1 : old_idx == 2 ? r2 : r3; ++old_idx; }
-        }
-        r0 = nr[0]; r1 = nr[1]; r2 = nr[2]; r3 = nr[3];
+        for (uint32_t k = 0; k < 3; ++k)
+          if (k < j && pbj) pbj &= 0x7fffffffu >> __clz((int)pbj);      // drop the highest set bit
+        const uint32_t from_new = __shfl_sync(kFull, dist, pbj ? 31 - __clz((int)pbj) : 0);
+        const uint32_t from_old = __shfl_sync(kFull, ringv, (int)((j - (uint32_t)__popc(push)) & 3u));
+        ringv = pbj ? from_new : from_old;
       }
       dx = dist;
     }
-    // ---- positions: one 64-bit warp scan gives every command its output and literal offsets
-    const uint64_t incl_both = warp_incl_scan64(((uint64_t)(ins + cpy) << 32) | ins, lane);
+    // ---- positions: one warp scan gives every command its output and literal offsets. Unless a command carries a
+    //      long run, both sums travel in one 32-bit word (bytes produced | literals << 16: 32 x 2046 < 2^16) -- the
+    //      very word the consumer gets.
+    uint32_t incl_tot, incl_ins, round_ins, round_out, pkv = 0;
+    const bool big = __any_sync(kFull, (ins | cpy) > 1023u);
+    if (!big) {
+      pkv = warp_incl_scan((ins + cpy) | (ins << 16), lane);
+      const uint32_t last = __shfl_sync(kFull, pkv, 31);
+      incl_tot = pkv & 0xffffu; incl_ins = pkv >> 16;
+      round_out = last & 0xffffu; round_ins = last >> 16;
+    } else {
+      const uint64_t incl_both = warp_incl_scan64(((uint64_t)(ins + cpy) << 32) | ins, lane);
+      incl_tot = (uint32_t)(incl_both >> 32); incl_ins = (uint32_t)incl_both;
+      round_ins = __shfl_sync(kFull, incl_ins, 31);
+      round_out = __shfl_sync(kFull, incl_tot, 31);
+    }
+    (void)incl_ins;
     // ---- literals of this round (PageDecoder.cpp:196-206)
-    const uint32_t round_ins = __shfl_sync(kFull, (uint32_t)incl_both, 31);
-    const uint32_t round_out = __shfl_sync(kFull, (uint32_t)(incl_both >> 32), 31);
     const uint32_t avail = lit_tail - lit_head_p;     // decoded ahead of need in earlier rounds (< 32)
     const uint32_t need = round_ins > avail ? round_ins - avail : 0u;
     const uint32_t mult = n ? (n == 32u ? (need + 31u) >> 5 : (need + n - 1u) / n) : 0u;
     const uint32_t rl = n * mult;                     // literals the stream carries for this round
     uint32_t mine = rl > lane ? (rl - lane + 31u) >> 5 : 0u;   // literal indices lit_tail + j*32 + lane
-    // a producer-side position check bounds the work a corrupt stream can ask for (the consumer checks too)
-    pos_p += round_out;
-    if (round_out > out_size || pos_p > out_size) {
-      if (lane == 0) { ctl->err = kPageErrOverrun; ctl->rflags[q] = kFlagAbort; }
-      warp_arrive(full_a + 8u * q, lane);
-      break;
+    {
+      // every command is validated here, so the consumer only ever sees rounds it can execute blindly: the page
+      // must hold the round, and a match must start inside the page (PageDecoder.cpp:222-232 trusts both)
+      const uint32_t o_cpy_page = pos_p + incl_tot - cpy;   // page offset where this command's copy lands
+      const uint32_t baddist = __ballot_sync(kFull, cpy != 0u && (dx == 0u || dx > o_cpy_page));
+      pos_p += round_out;
+      if (round_out > out_size || pos_p > out_size) { publish_abort(kPageErrOverrun); break; }
+      if (baddist) { publish_abort(kPageErrDistance); break; }
     }
-    bool fast = round_out <= kRoundMax && rl <= kLitQ;
+    bool fast = !big && round_out <= kRoundMax && rl <= kLitQ;
     if (fast) fast = wait_lit_room(rl);
     BGX_STAT(emu_stats().rounds++; emu_stats().lits += rl; if (!fast) emu_stats().slow_rounds++);
     if (fast) {
-      if (lane == 0) ctl->phead[q] = lit_head_p;   // literal head at the start of this round
+      if (lane == 0) ctl->phead[rnd & (kQ - 1u)] = lit_head_p;   // literal head at the start of this round
       decode_literals(sm, rd, in, lit_tail, mine, lane);
       lit_tail += rl;
       lit_head_p += round_ins;
-      publish(dx, (uint32_t)(incl_both >> 32) | ((uint32_t)incl_both << 16), pdone ? kFlagLast : 0u);
+      publish(dx, pkv, pdone ? kPkLast : 0u);
     } else {
       // ---- a round with long runs (more output than the ring path takes at once, or more literals than the
       //      literal ring holds) is handed over as a sequence of VIRTUAL rounds that each fit: a virtual round
@@ -949,9 +979,7 @@ BGX_DEV void producer_warp(const PageJob& job, WarpSmem* sm) {
       bool first = true, aborted = false;
       for (;;) {
         const uint32_t work = __ballot_sync(kFull, (rem_ins | rem_cpy) != 0u);
-        if (!first) {
-          if (!acquire_slot()) { aborted = true; break; }
-        }
+        if (!first) acquire_slot();
         first = false;
         const uint32_t qv = rnd & (kQ - 1u);
         const uint32_t a0 = work ? (uint32_t)(__ffs((int)work) - 1) : 32u;   // first command with something left
@@ -979,8 +1007,7 @@ BGX_DEV void producer_warp(const PageJob& job, WarpSmem* sm) {
         const uint32_t c = last_virtual ? s_mine : (s_mine < rows ? s_mine : rows);
         const uint32_t total = __reduce_add_sync(kFull, c);
         if (have + total < vr_ins || !wait_lit_room(total)) {   // the stream does not carry the literals it inserts
-          if (lane == 0) { ctl->err = kPageErrLiterals; ctl->rflags[qv] = kFlagAbort; }
-          warp_arrive(full_a + 8u * qv, lane);
+          publish_abort(kPageErrLiterals);
           aborted = true;
           break;
         }
@@ -989,7 +1016,7 @@ BGX_DEV void producer_warp(const PageJob& job, WarpSmem* sm) {
         s_mine -= c;
         lit_tail += total;
         lit_head_p += vr_ins;
-        publish(dx, (uint32_t)(vpk >> 32) | ((uint32_t)vpk << 16), (last_virtual && pdone) ? kFlagLast : 0u);
+        publish(dx, (uint32_t)(vpk >> 32) | ((uint32_t)vpk << 16), (last_virtual && pdone) ? kPkLast : 0u);
         if (last_virtual) break;
       }
       if (aborted) break;
@@ -999,68 +1026,55 @@ BGX_DEV void producer_warp(const PageJob& job, WarpSmem* sm) {
 }
 
 // ------------------------------------------------------------------------------------- CONSUMER
+// Positions are kept in "v-space": v = page offset + skew, skew = (output address & 15), so that v % 16 == 0 is
+// a 16-byte boundary of global memory whatever the caller's pointer is (word loads of far matches and the vector
+// flush are then always aligned). Every round the consumer sees was validated by the producer (it fits the page,
+// every match starts inside the page), so nothing here can fail.
+#ifndef BGX_PIECE_BATCH
+#define BGX_PIECE_BATCH 4
+#endif
+constexpr int kPieceBatch = BGX_PIECE_BATCH;   // chunks (of 32 pieces) whose source loads are issued back to back
+
 BGX_DEV void consumer_warp(const PageJob& job, WarpSmem* sm) {
-  const uint32_t lane = lane_id();
-  const uint32_t lt_mask = (1u << lane) - 1u;
-  const uint32_t le_mask = 0xffffffffu >> (31u - lane);
-  PageCtl* ctl = &sm->ctl;
-  uint8_t* const out = job.out;
-  const uint32_t out_size = job.out_size;
-  uint32_t pos = 0;            // bytes of the page produced so far
-  uint32_t flushed = 0;        // bytes already in global memory
-  int32_t ring_from = 0;       // ring holds valid data for positions >= ring_from (and > end - kRing)
+  const uint32_t lane = pinned(lane_id());
+  const uint32_t lt_mask = pinned((1u << lane) - 1u);
+  const uint32_t le_mask = pinned(0xffffffffu >> (31u - lane));
+  const uint32_t skew = (uint32_t)(reinterpret_cast<uintptr_t>(job.out) & 15u);
+  uint8_t* const outb = job.out - skew;     // 16-byte aligned: byte v of the page lives at outb[v]
+  const uint32_t end_v = skew + job.out_size;
+  uint32_t pos = skew;         // v of the next byte to produce
+  uint32_t flushed = skew;     // bytes below are in global memory
   uint32_t lit_head = 0;       // page-global literal index of the next literal to place
-  bool failed = false;         // a round was rejected: only keep the hand-over going until the producer stops
-  const bool out_aligned = (reinterpret_cast<uintptr_t>(out) & 15u) == 0;
-  const bool out_al4 = (reinterpret_cast<uintptr_t>(out) & 3u) == 0;
-  const saddr_t full_a = saddr(sm->mbar), empty_a = full_a + 8u * kQ;
+  const saddr_t sb = saddr_pinned(sm);       // one base register; everything else is a constant offset from it
+  const saddr_t full_a = sb + (uint32_t)offsetof(WarpSmem, mbar), empty_a = full_a + 8u * kQ;
+  const saddr_t ring_a = sb + (uint32_t)offsetof(WarpSmem, ring), litq_a = sb + (uint32_t)offsetof(WarpSmem, litq);
+  const saddr_t tab_a = sb + (uint32_t)offsetof(WarpSmem, scratch), rb_a = sb + (uint32_t)offsetof(WarpSmem, rb);
+  const saddr_t tab2_a = tab_a + 128u;
 
   for (uint32_t r = 0;; ++r) {
     const uint32_t q = r & (kQ - 1u);
     mbar_wait(full_a + 8u * q, (r / kQ) & 1u);
-    const uint32_t rflags = ctl->rflags[q];
-    if ((rflags & kFlagAbort) || failed) {
-      if (rflags & kFlagAbort) break;
-      warp_arrive(empty_a + 8u * q, lane);
-      if (rflags & kFlagLast) break;
-      continue;
-    }
-    const RoundBuf* rb = &sm->rb[q];
-    const uint32_t pk = rb->pk[lane];
-    const uint32_t dist = rb->dx[lane];            // resolved by the producer
-    const uint32_t pk_last = rb->pk[31];
+    const uint2 cw = lds_u32x2(rb_a + (uint32_t)sizeof(RoundBuf) * q + 8u * lane);
+    if (cw.y & kPkAbort) break;
+    const uint32_t dist = cw.x;                        // resolved and validated by the producer
+    const uint32_t pk = cw.y & kPkSums;
     uint32_t pk_prev = __shfl_up_sync(kFull, pk, 1);
     if (lane == 0) pk_prev = 0;
-    const uint32_t incl_tot = pk & 0xffffu, incl_ins = pk >> 16;
-    const uint32_t tot = incl_tot - (pk_prev & 0xffffu);
-    const uint32_t ins = incl_ins - (pk_prev >> 16);
-    const uint32_t cpy = tot - ins;
-    const bool has_copy = cpy != 0;
+    const uint32_t pk_last = __shfl_sync(kFull, pk, 31);
+    const uint32_t lq = pk_prev >> 16;                 // round-local index of this command's first literal
+    const uint32_t ins = (pk >> 16) - lq;
+    const uint32_t cpy = (pk & 0xffffu) - (pk_prev & 0xffffu) - ins;
     const uint32_t round_out = pk_last & 0xffffu;
     const uint32_t round_ins = pk_last >> 16;
-    const uint32_t o_ins = pos + incl_tot - tot;        // where this command's literals go
-    const uint32_t o_cpy = o_ins + ins;                 // where its copy goes
+    const uint32_t o_ins = pos + (pk_prev & 0xffffu);  // where this command's literals go
+    const uint32_t o_cpy = o_ins + ins;                // where its copy goes
     const uint32_t round_end = pos + round_out;
-    {
-      uint32_t err = 0;
-      if (round_out > out_size - pos) err = kPageErrOverrun;
-      const uint32_t baddist = __ballot_sync(kFull, has_copy && (dist == 0 || dist > o_cpy));
-      if (baddist && !err) err = kPageErrDistance;
-      if (err) {
-        if (lane == 0) ctl->err = err;
-        failed = true;
-        warp_arrive(empty_a + 8u * q, lane);
-        if (rflags & kFlagLast) break;
-        continue;
-      }
-    }
-    const uint32_t lq = incl_ins - ins;                // round-local index of this command's first literal
-    const int32_t ring_lo = ring_from > (int32_t)round_end - (int32_t)kRing ? ring_from : (int32_t)round_end - (int32_t)kRing;
+    const int32_t ring_lo = (int32_t)skew > (int32_t)round_end - (int32_t)kRing ? (int32_t)skew : (int32_t)round_end - (int32_t)kRing;
 #ifdef BGX_STATS
     {
       const uint32_t mi = __reduce_max_sync(kFull, ins < kCoopLen ? ins : 0u);
       const uint32_t ncp = __popc(__ballot_sync(kFull, cpy != 0));
-      const uint32_t far = __reduce_add_sync(kFull, (cpy && dist > 1500u) ? cpy : 0u);
+      const uint32_t far = __reduce_add_sync(kFull, (cpy && (int32_t)(o_cpy - dist) < ring_lo) ? cpy : 0u);
       const uint32_t ov = __popc(__ballot_sync(kFull, cpy != 0 && dist < cpy));
       BGX_STAT(emu_stats().sum_max_ins += mi; emu_stats().ins_bytes += round_ins; emu_stats().copies += ncp;
                emu_stats().copy_bytes += round_out - round_ins; emu_stats().far_bytes += far; emu_stats().overlap_copies += ov);
@@ -1069,196 +1083,152 @@ BGX_DEV void consumer_warp(const PageJob& job, WarpSmem* sm) {
     // ---- inserts, flattened: lane t places literal t of the round (perfectly balanced, any length).
     //      Commands with literals are compacted into tab[]; a per-chunk bit mask of their first
     //      literal index turns "which command owns literal t" into one popc.
-    uint32_t* tab = sm->scratch;                       // [32] (o_ins - first literal index)
-    const saddr_t ring_a = saddr(sm->ring), litq_a = saddr(sm->litq), tab_a = saddr(sm->scratch);
-#ifdef BGX_INS_PIECES
-    // EXPERIMENT (off by default, not yet measured on the GPU): literal-heavy rounds (>= BGX_INS_PIECES literals, e.g.
-    // the 256-literal virtual rounds of noisy data) place their literals as 4-byte pieces, like the ready copies:
-    // the literals of one command are contiguous in the literal ring and in the output.
-    if (round_ins >= (uint32_t)(BGX_INS_PIECES)) {
-      const uint32_t np = (ins + 3u) >> 2;
-      const uint32_t E = warp_incl_scan(np, lane);
-      const uint32_t T = __shfl_sync(kFull, E, 31);
-      const uint32_t S = E - np;
+    if (round_ins) {
       const uint32_t has = __ballot_sync(kFull, ins != 0);
-      // entry: (dst - 4 * first piece index, literal index of the first literal - 4 * first piece index | (end - that) << 17)
-      uint2* tabp = reinterpret_cast<uint2*>(sm->scratch + 32);
-      if (ins) tabp[__popc(has & lt_mask)] = make_uint2(o_ins - 4u * S, ((lit_head + lq - 4u * S) & 0x1ffffu) | ((4u * S + ins) << 17));
-      __syncwarp();
-      const uint32_t pcidx = S >> 5;
-      const uint32_t pcbit = ins ? (1u << (S & 31u)) : 0u;
-      const uint32_t plast = __popc(has) - 1u;
-      uint32_t before = 0;
-#pragma unroll 1
-      for (uint32_t c = 0, t = lane; 32u * c < T; ++c, t += 32u) {
-        const uint32_t M = __reduce_or_sync(kFull, pcidx == c ? pcbit : 0u);
-        uint32_t ord = before + __popc(M & le_mask) - 1u;
-        before += __popc(M);
-        ord = ord < plast ? ord : plast;
-        const uint2 e = lds_u32x2(tab_a + 128u + 8u * ord);
-        const uint32_t d = e.x + 4u * t;
-        const uint32_t li = (e.y & 0x1ffffu) + 4u * t;                 // literal index (mod 2^17; the ring is 512)
-        int32_t rem = (int32_t)((e.y >> 17) - 4u * t);
-        if (t >= T) rem = 0;
-        const uint32_t a = li & (kLitQ - 4u);
-        const uint32_t lo = lds_u32(litq_a + a);
-        const uint32_t hi = lds_u32(litq_a + ((a + 4u) & (kLitQ - 1)));
-        const uint32_t v = __funnelshift_r(lo, hi, (li & 3u) * 8u);
-        if (rem > 0) sts_u8(ring_a + (d & (kRing - 1)), v);
-        if (rem > 1) sts_u8(ring_a + ((d + 1u) & (kRing - 1)), v >> 8);
-        if (rem > 2) sts_u8(ring_a + ((d + 2u) & (kRing - 1)), v >> 16);
-        if (rem > 3) sts_u8(ring_a + ((d + 3u) & (kRing - 1)), v >> 24);
-      }
-    } else
-#endif
-    {
-      const uint32_t has = __ballot_sync(kFull, ins != 0);
-      if (ins) tab[__popc(has & lt_mask)] = o_ins - lq;
+      if (ins) sts_u32(tab_a + 4u * __popc(has & lt_mask), o_ins - lq);
       __syncwarp();
       const uint32_t icidx = lq >> 5;
       const uint32_t icbit = ins ? (1u << (lq & 31u)) : 0u;
       const uint32_t ilast = __popc(has) - 1u;
       uint32_t before = 0;
-      for (uint32_t c = 0, c0 = 0; c0 < round_ins; ++c, c0 += 32) {
+#pragma unroll 1
+      for (uint32_t c = 0, t = lane; 32u * c < round_ins; ++c, t += 32u) {
         const uint32_t M = __reduce_or_sync(kFull, icidx == c ? icbit : 0u);
-        const uint32_t t = c0 + lane;
         uint32_t ord = before + __popc(M & le_mask) - 1u;
         before += __popc(M);
         ord = ord < ilast ? ord : ilast;
         const uint32_t base = lds_u32(tab_a + 4u * ord);
         if (t < round_ins)   // (lanes past the round's last literal must not touch slots the producer is filling)
-          sts_u8(ring_a + ((base + t) & (kRing - 1)), lds_u8(litq_a + ((lit_head + t) & (kLitQ - 1))));
+          sts_u8(ring_at(ring_a, base + t), lds_u8(litq_at(litq_a, lit_head + t)));
       }
     }
     warp_arrive(empty_a + 8u * q, lane);   // the RoundBuf and this round's literals are no longer needed
-    // ---- copies. Wavefront 1: every copy whose source already is final, i.e. lies below the destination of
-    //      the first pending copy, flattened over 4-byte PIECES: lane t moves piece t of the wavefront
-    //      (perfectly balanced, any length mix). Ready copies are compacted into tab2[]; a per-chunk bit
-    //      mask of their first piece index turns "which copy owns piece t" into one popc. A piece is
-    //      fetched as two aligned words + a funnel shift, from the ring (near) or from L1/L2 (far matches;
-    //      everything below `flushed` is in global memory, and flushed >= ring_lo + 4 always holds).
+    // ---- copies. Wave 1: every copy whose source already is final, i.e. lies below the destination of the first
+    //      copy of the round (or is that copy), flattened over 4-byte PIECES: lane t moves piece t of the wave
+    //      (perfectly balanced, any length mix). Ready copies are compacted into tab2[]; a per-chunk bit mask of
+    //      their first piece index turns "which copy owns piece t" into one popc. A piece is fetched as two aligned
+    //      words + a funnel shift, from the ring (near) or from L2 (far matches: everything below `flushed` is in
+    //      global memory, and ring_lo + 512 < flushed). The source words of up to kPieceBatch chunks are requested
+    //      back to back before the first of them is stored (the pieces of a wave are independent), so that the
+    //      round pays the L2 latency of its far matches once, not once per chunk.
     uint32_t pending = __ballot_sync(kFull, cpy != 0);
     if (pending) {
-      const int first = __ffs((int)pending) - 1;
-      const uint32_t hwm = __shfl_sync(kFull, o_cpy, first);           // everything below is final
-      const bool ready1 = cpy != 0 && dist >= cpy && ((int)lane == first || o_cpy - dist + cpy <= hwm);
+      const uint32_t first = (uint32_t)__ffs((int)pending) - 1u;
+      const uint32_t hwm = __shfl_sync(kFull, o_cpy, (int)first);      // everything below is final
+      const bool ready1 = cpy != 0 && dist >= cpy && (lane == first || o_cpy - dist + cpy <= hwm);
       const uint32_t np1 = ready1 ? (cpy + 3u) >> 2 : 0u;
       const uint32_t E1 = warp_incl_scan(np1, lane);
       const uint32_t T1 = __shfl_sync(kFull, E1, 31);
       const uint32_t S1 = E1 - np1;
       const uint32_t m1 = __ballot_sync(kFull, ready1);
-      // entry: (dst - 4 * first piece index, distance | (end - that) << 17); page <= 128 KiB, round <= kRoundMax
-      uint2* tab2 = reinterpret_cast<uint2*>(sm->scratch + 32);        // [32]
-      if (ready1) tab2[__popc(m1 & lt_mask)] = make_uint2(o_cpy - 4u * S1, dist | ((4u * S1 + cpy) << 17));
+      pending &= ~m1;
+      // wave-1 entry: (dst - 4 * first piece index, distance | (end - that) << 17); page <= 128 KiB, round <= kRoundMax
+      if (ready1) sts_u32x2(tab2_a + 8u * __popc(m1 & lt_mask), o_cpy - 4u * S1, dist | ((4u * S1 + cpy) << 17));
+      // the others, in command order: dst - round start (< 1024) | length (<= 1024) << 10 | distance (< 1024) << 21.
+      // A copy that is not in wave 1 overlaps itself or reads bytes of this round, so its distance is < kRoundMax.
+      else if (cpy) sts_u32(tab_a + 4u * __popc(pending & lt_mask), (o_cpy - pos) | (cpy << 10) | (dist << 21));
       __syncwarp();
       const uint32_t cidx = S1 >> 5;
       const uint32_t cbit = ready1 ? (1u << (S1 & 31u)) : 0u;
       const uint32_t last = __popc(m1) - 1u;
-      const saddr_t tab2_a = tab_a + 128u;
       uint32_t before = 0;
-      // fetch: owner look-up + the two source words of piece t; place: the (up to) four byte stores
-      auto fetch = [&](uint32_t c, uint32_t t, uint32_t& d, int32_t& rem, uint32_t& lo, uint32_t& hi, uint32_t& sh) {
-        const uint32_t M = __reduce_or_sync(kFull, cidx == c ? cbit : 0u);
-        uint32_t ord = before + __popc(M & le_mask) - 1u;
-        before += __popc(M);
-        ord = ord < last ? ord : last;                                 // lanes past the end read a valid entry
-        const uint2 e = lds_u32x2(tab2_a + 8u * ord);
-        d = e.x + 4u * t;                                              // destination of this piece
-        const uint32_t sp = d - (e.y & 0x1ffffu);                      // its source
-        rem = (int32_t)((e.y >> 17) - 4u * t);                         // bytes of the copy from this piece on
-        if (t >= T1) rem = 0;
-        lo = 0; hi = 0;
-        sh = (sp & 3u) * 8u;
-        if (rem > 0) {
-          if ((int32_t)sp >= ring_lo) {
-            const uint32_t a = sp & (kRing - 4u);
-            lo = lds_u32(ring_a + a);
-            hi = lds_u32(ring_a + ((a + 4u) & (kRing - 1)));
-          } else if (out_al4) {
-            const uint32_t* g = reinterpret_cast<const uint32_t*>(out + (sp & ~3u));
-            lo = ldg_u32(g);
-            if ((sp & 3u) + (uint32_t)rem > 4u) hi = ldg_u32(g + 1);   // only when it holds a byte of the source
-          } else {
-            lo = ldg_u8(out + sp);
-            if (rem > 1) lo |= ldg_u8(out + sp + 1) << 8;
-            if (rem > 2) lo |= ldg_u8(out + sp + 2) << 16;
-            if (rem > 3) lo |= ldg_u8(out + sp + 3) << 24;
-            sh = 0;
+#pragma unroll 1
+      for (uint32_t c0 = 0; 32u * c0 < T1; c0 += kPieceBatch) {
+        uint32_t w0[kPieceBatch], w1[kPieceBatch], meta[kPieceBatch];
+#pragma unroll
+        for (int u = 0; u < kPieceBatch; ++u) {
+          const uint32_t c = c0 + (uint32_t)u;
+          meta[u] = 0; w0[u] = 0; w1[u] = 0;
+          if (32u * c < T1) {                                           // (uniform)
+            const uint32_t t4 = 128u * c + 4u * lane;
+            const uint32_t M = __reduce_or_sync(kFull, cidx == c ? cbit : 0u);
+            uint32_t ord = before + __popc(M & le_mask) - 1u;
+            before += __popc(M);
+            ord = ord < last ? ord : last;                              // lanes past the end read a valid entry
+            const uint2 e = lds_u32x2(tab2_a + 8u * ord);
+            const uint32_t d = e.x + t4;                                // destination of this piece
+            const uint32_t sp = d - (e.y & 0x1ffffu);                   // its source
+            int32_t rem = (int32_t)((e.y >> 17) - t4);                  // bytes of the copy from this piece on (<= 0 past the end)
+            rem = rem > 4 ? 4 : rem;
+            if (rem > 0) {
+              if ((int32_t)sp >= ring_lo) {
+                w0[u] = lds_u32(ring_at(ring_a, sp & ~3u));
+                w1[u] = lds_u32(ring_at(ring_a, (sp & ~3u) + 4u));
+              } else {
+                const uint32_t* g = reinterpret_cast<const uint32_t*>(outb + (sp & ~3u));
+                w0[u] = ldg_u32(g);
+                w1[u] = ldg_u32(g + 1);
+              }
+              meta[u] = ((sp & 3u) << 3) | ((uint32_t)rem << 5) | ((d & (kRing - 1u)) << 8);
+            }
           }
         }
-      };
-      auto place = [&](uint32_t d, int32_t rem, uint32_t lo, uint32_t hi, uint32_t sh) {
-        const uint32_t v = __funnelshift_r(lo, hi, sh);
-        if (rem > 0) sts_u8(ring_a + (d & (kRing - 1)), v);
-        if (rem > 1) sts_u8(ring_a + ((d + 1u) & (kRing - 1)), v >> 8);
-        if (rem > 2) sts_u8(ring_a + ((d + 2u) & (kRing - 1)), v >> 16);
-        if (rem > 3) sts_u8(ring_a + ((d + 3u) & (kRing - 1)), v >> 24);
-      };
-#pragma unroll 1
-      for (uint32_t c = 0, t = lane; 32u * c < T1; ++c, t += 32u) {
-        uint32_t d, lo, hi, sh;
-        int32_t rem;
-        fetch(c, t, d, rem, lo, hi, sh);
-        place(d, rem, lo, hi, sh);
-      }
-      __syncwarp();
-      pending &= ~m1;
-    }
-    //      Remaining copies (dependent on this round's copies, or overlapping themselves): in command
-    //      order, each by the whole warp (lane j moves byte j; almost always a single step). In-order
-    //      execution satisfies every dependency; an overlapping copy (dist < len) repeats its
-    //      `dist`-byte pattern exactly as the byte-serial reference loop does (PageDecoder.cpp:222-232).
-#pragma unroll 1
-    while (pending) {
-      const int k = __ffs((int)pending) - 1;
-      pending &= pending - 1;
-      const uint32_t n_k = __shfl_sync(kFull, cpy, k);
-      const uint32_t o_k = __shfl_sync(kFull, o_cpy, k);
-      const uint32_t d_k = __shfl_sync(kFull, dist, k);
-      BGX_STAT(emu_stats().wavefronts++; emu_stats().sum_max_cpy += n_k);
-      if (n_k <= 32u && d_k >= n_k) {                                  // the usual case: one step, no overlap
-        if (lane < n_k) {
-          const uint32_t sp = o_k - d_k + lane;
-          const uint32_t v = ((int32_t)sp >= ring_lo) ? lds_u8(ring_a + (sp & (kRing - 1))) : ldg_u8(out + sp);
-          sts_u8(ring_a + ((o_k + lane) & (kRing - 1)), v);
-        }
-      } else {
-#pragma unroll 1
-        for (uint32_t j = lane; j < n_k; j += 32) {
-          const uint32_t m = j < d_k ? j : j % d_k;
-          const uint32_t sp = o_k - d_k + m;
-          const uint32_t v = ((int32_t)sp >= ring_lo) ? lds_u8(ring_a + (sp & (kRing - 1))) : ldg_u8(out + sp);
-          sts_u8(ring_a + ((o_k + j) & (kRing - 1)), v);
+#pragma unroll
+        for (int u = 0; u < kPieceBatch; ++u) {
+          const uint32_t m = meta[u];
+          const uint32_t v = __funnelshift_r(w0[u], w1[u], m);          // (shift = low five bits = 8 * (source & 3))
+          const uint32_t dd = m >> 8;                                    // ring offset of the piece's first byte
+          const saddr_t a = ring_a + dd;
+          if (dd <= kRing - 4u) {                                        // (all but 3 in 2048 pieces: no wrap inside the piece)
+            if (m & (7u << 5)) sts_u8(a, v);
+            if (m & (6u << 5)) sts_u8(a + 1u, v >> 8);                   // rem >= 2
+            if ((m & (7u << 5)) >= (3u << 5)) sts_u8(a + 2u, v >> 16);
+            if (m & (4u << 5)) sts_u8(a + 3u, v >> 24);                  // rem == 4
+          } else {
+            if (m & (7u << 5)) sts_u8(a, v);
+            if (m & (6u << 5)) sts_u8(ring_at(ring_a, dd + 1u), v >> 8);
+            if ((m & (7u << 5)) >= (3u << 5)) sts_u8(ring_at(ring_a, dd + 2u), v >> 16);
+            if (m & (4u << 5)) sts_u8(ring_at(ring_a, dd + 3u), v >> 24);
+          }
         }
       }
       __syncwarp();
+      //    The remaining copies (they read bytes of this round's copies, or overlap themselves): in command order,
+      //    each by the whole warp (lane j moves byte j; almost always a single step). In-order execution satisfies
+      //    every dependency; an overlapping copy (dist < len) repeats its `dist`-byte pattern exactly as the
+      //    byte-serial reference loop does (PageDecoder.cpp:222-232). Their sources lie inside the ring.
+      const uint32_t npend = __popc(pending);
+      if (npend) {
+        uint32_t e = lds_u32(tab_a);
+#pragma unroll 1
+        for (uint32_t i = 0; i < npend; ++i) {
+          const uint32_t e_next = lds_u32(tab_a + 4u * (i + 1u < npend ? i + 1u : i));
+          const uint32_t o_k = pos + (e & 1023u), n_k = (e >> 10) & 2047u, d_k = e >> 21;
+          BGX_STAT(emu_stats().wavefronts++; emu_stats().sum_max_cpy += n_k);
+          if (n_k <= 32u && d_k >= n_k) {                                  // the usual case: one step, no overlap
+            if (lane < n_k) sts_u8(ring_at(ring_a, o_k + lane), lds_u8(ring_at(ring_a, o_k - d_k + lane)));
+          } else {
+#pragma unroll 1
+            for (uint32_t j = lane; j < n_k; j += 32) {
+              const uint32_t mj = j < d_k ? j : j % d_k;
+              sts_u8(ring_at(ring_a, o_k + j), lds_u8(ring_at(ring_a, o_k - d_k + mj)));
+            }
+          }
+          __syncwarp();
+          e = e_next;
+        }
+      }
     }
     pos = round_end;
     lit_head += round_ins;
-    // ---- write-combined flush of complete 512-byte chunks
+    // ---- write-combined flush of complete 512-byte chunks (16 bytes per lane; v % 16 == 0 is a 16-byte boundary)
     if (pos - flushed >= kFlushChunk) {
-      if (out_aligned) {
-        if (flushed & 15u) {   // after a cooperative (direct) episode the flush point may be unaligned
-          const uint32_t to = (flushed + 15u) & ~15u;
-          flush_bytes(sm, out, flushed, to, lane);
-          flushed = to;
-        }
-        while (pos - flushed >= kFlushChunk) {
-          const uint32_t f = flushed + 16u * lane;
-          *reinterpret_cast<uint4*>(out + f) = *reinterpret_cast<const uint4*>(&sm->ring[f & (kRing - 1)]);
-          flushed += kFlushChunk;
-        }
-      } else {
-        const uint32_t to = flushed + ((pos - flushed) / kFlushChunk) * kFlushChunk;
-        flush_bytes(sm, out, flushed, to, lane);
+      if (flushed & 15u) {   // page start of an unaligned output buffer
+        const uint32_t to = (flushed + 15u) & ~15u;
+        flush_bytes(sm, outb, flushed, to, lane);
         flushed = to;
+      }
+      while (pos - flushed >= kFlushChunk) {
+        const uint32_t f = flushed + 16u * lane;
+        *reinterpret_cast<uint4*>(outb + f) = *reinterpret_cast<const uint4*>(&sm->ring[f & (kRing - 1)]);
+        flushed += kFlushChunk;
       }
       __syncwarp();
     }
-    if (rflags & kFlagLast) {
+    if (cw.y & kPkLast) {
       // ---- last round: whatever is still only in the ring, then zero-fill (the reference memsets the page first)
-      flush_bytes(sm, out, flushed, pos, lane);
-      for (uint32_t z = pos + lane; z < out_size; z += 32) out[z] = 0;
+      flush_bytes(sm, outb, flushed, pos, lane);
+      for (uint32_t z = pos + lane; z < end_v; z += 32) outb[z] = 0;
       break;
     }
   }
