@@ -55,6 +55,7 @@ __global__ void __launch_bounds__(kPageThreads, BGX_CTAS_PER_SM) bgx_decode_page
   __shared__ uint32_t q_shared;
   const uint32_t tid = threadIdx.x;
   uint32_t cur_stream = 0;   // owner of the last page this CTA decoded (streams are in queue order)
+  bool first_compressed = true;   // the page arena's mbarriers have not been initialised yet
   if (tid == 0) q_shared = atomicAdd(&ctl->next_page, 1u);
   for (;;) {
     __syncthreads();
@@ -113,7 +114,8 @@ __global__ void __launch_bounds__(kPageThreads, BGX_CTAS_PER_SM) bgx_decode_page
       job.out = out;
       job.out_size = e.out_size;
       job.allow_delta = s.allow_delta;
-      const bgxk::PageResult r = bgxk::decode_page_cta(job, &sm);
+      const bgxk::PageResult r = bgxk::decode_page_cta(job, &sm, first_compressed);
+      first_compressed = false;
       status = r.status;
       if (!status && r.is_delta) {
         if (tid >= 32) bgxk::delta_decode_warp(out, e.out_off, e.out_size, s.planes);   // the consumer warp wrote the page
@@ -185,6 +187,10 @@ struct bgx_context {
   size_t d_out_cap = 0;
   uint8_t* d_scratch = nullptr;   // conditioned planes of texture streams decoded through the host-pointer calls
   size_t d_scratch_cap = 0;
+  uint8_t* d_meta = nullptr;      // work descriptors / queue control / page status of the host-pointer calls' plans
+  size_t d_meta_cap = 0;
+  std::vector<cudaEvent_t> ev_pool;   // timing events of the host-pointer pipeline (created once, reused by every call)
+  cudaEvent_t ev_start = nullptr;
 };
 
 struct PreconJob {
@@ -206,6 +212,7 @@ struct bgx_plan {
   std::vector<PreconJob> precon;
   uint8_t* d_scratch = nullptr;   // backing store of all conditioned scratch planes
   bool owns_scratch = true;       // false: borrowed from the context's grow-only arena (host-pointer calls)
+  bool owns_meta = true;          // false: d_streams / d_ctl / d_status / d_layouts / d_precon are carved from ctx->d_meta
   PreconDev* d_precon = nullptr;  // device copy of the pre-conditioned jobs, in stream order
   PreconLayout* d_layouts = nullptr;   // their layouts, one array
   bgx_plan_info info{};
@@ -299,6 +306,9 @@ void bgx_destroy(bgx_context* ctx) {
   if (ctx->d_in) cudaFree(ctx->d_in);
   if (ctx->d_out) cudaFree(ctx->d_out);
   if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+  if (ctx->d_meta) cudaFree(ctx->d_meta);
+  for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
+  if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -311,12 +321,14 @@ const char* bgx_last_error(const bgx_context* ctx) { return ctx ? ctx->err.c_str
 
 void bgx_plan_destroy(bgx_plan* plan) {
   if (!plan) return;
-  if (plan->d_streams) cudaFree(plan->d_streams);
-  if (plan->d_ctl) cudaFree(plan->d_ctl);
-  if (plan->d_status) cudaFree(plan->d_status);
+  if (plan->owns_meta) {
+    if (plan->d_streams) cudaFree(plan->d_streams);
+    if (plan->d_ctl) cudaFree(plan->d_ctl);
+    if (plan->d_status) cudaFree(plan->d_status);
+    if (plan->d_precon) cudaFree(plan->d_precon);
+    if (plan->d_layouts) cudaFree(plan->d_layouts);
+  }
   if (plan->d_scratch && plan->owns_scratch) cudaFree(plan->d_scratch);
-  if (plan->d_precon) cudaFree(plan->d_precon);
-  if (plan->d_layouts) cudaFree(plan->d_layouts);
   delete plan;
 }
 
@@ -396,6 +408,31 @@ static int plan_create_impl(bgx_context* ctx, const bgx_stream* streams, uint32_
     plan->info.uncompressed_bytes += produced;
   }
   plan->info.pages = plan->total_pages;
+  // device memory of the plan: per-plan allocations, or -- for the host-pointer calls, which build a plan per call --
+  // one grow-only arena of the context, so that a call costs no cudaMalloc once the arenas are warm
+  const size_t ns = std::max<size_t>(plan->h_streams.size(), 1);
+  const size_t np = plan->precon.size();
+  auto up256 = [](size_t n) { return (n + 255u) & ~(size_t)255u; };
+  const size_t sz_streams = up256(ns * sizeof(StreamDev)), sz_ctl = up256(kMaxGroups * sizeof(QueueCtl));
+  const size_t sz_status = up256(std::max<size_t>(plan->total_pages, 1) * sizeof(uint32_t));
+  const size_t sz_layouts = up256(np * sizeof(PreconLayout)), sz_precon = up256(np * sizeof(PreconDev));
+  if (ctx_scratch) {
+    if (grow(ctx, &ctx->d_meta, &ctx->d_meta_cap, sz_streams + sz_ctl + sz_status + sz_layouts + sz_precon)) return bgx::kErrGeneric;
+    uint8_t* p = ctx->d_meta;
+    plan->owns_meta = false;
+    plan->d_streams = reinterpret_cast<StreamDev*>(p); p += sz_streams;
+    plan->d_ctl = reinterpret_cast<QueueCtl*>(p); p += sz_ctl;
+    plan->d_status = reinterpret_cast<uint32_t*>(p); p += sz_status;
+    if (np) { plan->d_layouts = reinterpret_cast<PreconLayout*>(p); p += sz_layouts; plan->d_precon = reinterpret_cast<PreconDev*>(p); }
+  } else {
+    BGX_CUDA(ctx, cudaMalloc(&plan->d_streams, sz_streams));
+    BGX_CUDA(ctx, cudaMalloc(&plan->d_ctl, sz_ctl));
+    BGX_CUDA(ctx, cudaMalloc(&plan->d_status, sz_status));
+    if (np) {
+      BGX_CUDA(ctx, cudaMalloc(&plan->d_layouts, sz_layouts));
+      BGX_CUDA(ctx, cudaMalloc(&plan->d_precon, sz_precon));
+    }
+  }
   if (scratch_bytes) {
     if (ctx_scratch) {
       if (grow(ctx, &ctx->d_scratch, &ctx->d_scratch_cap, scratch_bytes)) return bgx::kErrGeneric;
@@ -412,10 +449,9 @@ static int plan_create_impl(bgx_context* ctx, const bgx_stream* streams, uint32_
         d.allow_delta = 1;
       }
     }
-    // all texture layouts of the plan in one device array (one allocation, one copy)
+    // all texture layouts of the plan in one device array (one copy)
     std::vector<PreconLayout> hl;
     for (auto& p : plan->precon) hl.push_back(p.layout);
-    BGX_CUDA(ctx, cudaMalloc(&plan->d_layouts, hl.size() * sizeof(PreconLayout)));
     BGX_CUDA(ctx, cudaMemcpy(plan->d_layouts, hl.data(), hl.size() * sizeof(PreconLayout), cudaMemcpyHostToDevice));
     std::vector<PreconDev> hj;
     for (size_t k = 0; k < plan->precon.size(); ++k) {
@@ -423,15 +459,10 @@ static int plan_create_impl(bgx_context* ctx, const bgx_stream* streams, uint32_
       p.d_layout = plan->d_layouts + k;
       hj.push_back(PreconDev{p.d_layout, p.d_planes, p.d_tex});
     }
-    BGX_CUDA(ctx, cudaMalloc(&plan->d_precon, hj.size() * sizeof(PreconDev)));
     BGX_CUDA(ctx, cudaMemcpy(plan->d_precon, hj.data(), hj.size() * sizeof(PreconDev), cudaMemcpyHostToDevice));
   }
-  const size_t ns = std::max<size_t>(plan->h_streams.size(), 1);
-  BGX_CUDA(ctx, cudaMalloc(&plan->d_streams, ns * sizeof(StreamDev)));
   if (!plan->h_streams.empty())
     BGX_CUDA(ctx, cudaMemcpy(plan->d_streams, plan->h_streams.data(), plan->h_streams.size() * sizeof(StreamDev), cudaMemcpyHostToDevice));
-  BGX_CUDA(ctx, cudaMalloc(&plan->d_ctl, kMaxGroups * sizeof(QueueCtl)));
-  BGX_CUDA(ctx, cudaMalloc(&plan->d_status, std::max<size_t>(plan->total_pages, 1) * sizeof(uint32_t)));
   plan->info.kernels_per_launch = (plan->total_pages ? 1u : 0u) + (plan->precon.empty() ? 0u : 1u);
   plan->info.sm_count = (uint32_t)ctx->sm_count;
   plan->info.block_threads = kPageThreads;
@@ -556,48 +587,57 @@ int bgx_decode_batch_host(bgx_context* ctx, uint32_t n, const uint8_t* const* in
   }
   const uint32_t G = (uint32_t)cut.size() - 1;
   plan->groups_used = G;
-  std::vector<cudaEvent_t> ev(3 * (size_t)G);
-  for (auto& e : ev) cudaEventCreate(&e);
-  cudaEvent_t ev_start;
-  cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming);
-  cudaEventRecord(ev_start, ctx->stream);              // arena growth / earlier work on the context stream
-  cudaStreamWaitEvent(ctx->s_in, ev_start, 0);
-  cudaStreamWaitEvent(ctx->s_out, ev_start, 0);
-  for (uint32_t g = 0; g < G && !rc; ++g) {
+  // every CUDA call of the pipeline is checked: a failed copy must not turn into a "successful" decode of stale bytes
+  struct PlanGuard { bgx_plan* p; ~PlanGuard() { bgx_plan_destroy(p); } } plan_guard{plan};
+  while (ctx->ev_pool.size() < 3 * (size_t)G) {
+    cudaEvent_t e;
+    BGX_CUDA(ctx, cudaEventCreate(&e));
+    ctx->ev_pool.push_back(e);
+  }
+  if (!ctx->ev_start) BGX_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_start, cudaEventDisableTiming));
+  const std::vector<cudaEvent_t>& ev = ctx->ev_pool;
+  BGX_CUDA(ctx, cudaEventRecord(ctx->ev_start, ctx->stream));              // arena growth / earlier work on the context stream
+  BGX_CUDA(ctx, cudaStreamWaitEvent(ctx->s_in, ctx->ev_start, 0));
+  BGX_CUDA(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->ev_start, 0));
+  cudaError_t pipe_err = cudaSuccess;
+  auto ok = [&](cudaError_t e) { if (e != cudaSuccess && pipe_err == cudaSuccess) pipe_err = e; return e == cudaSuccess; };
+  for (uint32_t g = 0; g < G && !rc && pipe_err == cudaSuccess; ++g) {
     cudaEvent_t e_in = ev[3 * g], e_k0 = ev[3 * g + 1], e_k1 = ev[3 * g + 2];
     for (uint32_t k = cut[g]; k < cut[g + 1]; ++k) {
       const Segment& sg = seg[k];
       if (sg.up1 > sg.up0)
-        cudaMemcpyAsync(ctx->d_in + in_off[sg.stream] + sg.up0, inputs[sg.stream] + sg.up0, sg.up1 - sg.up0, cudaMemcpyHostToDevice, ctx->s_in);
+        ok(cudaMemcpyAsync(ctx->d_in + in_off[sg.stream] + sg.up0, inputs[sg.stream] + sg.up0, sg.up1 - sg.up0, cudaMemcpyHostToDevice, ctx->s_in));
     }
-    cudaEventRecord(e_in, ctx->s_in);
-    cudaStreamWaitEvent(ctx->stream, e_in, 0);
-    cudaEventRecord(e_k0, ctx->stream);
+    ok(cudaEventRecord(e_in, ctx->s_in));
+    ok(cudaStreamWaitEvent(ctx->stream, e_in, 0));
+    ok(cudaEventRecord(e_k0, ctx->stream));
+    if (pipe_err != cudaSuccess) break;
     rc = launch_range(ctx, plan, cut[g], cut[g + 1], g, ctx->stream);
-    cudaEventRecord(e_k1, ctx->stream);
-    cudaStreamWaitEvent(ctx->s_out, e_k1, 0);
-    for (uint32_t k = cut[g]; k < cut[g + 1]; ++k) {
+    ok(cudaEventRecord(e_k1, ctx->stream));
+    ok(cudaStreamWaitEvent(ctx->s_out, e_k1, 0));
+    for (uint32_t k = cut[g]; k < cut[g + 1] && !rc; ++k) {
       const Segment& sg = seg[k];
       if (sg.dn1 > sg.dn0)
-        cudaMemcpyAsync(outputs[sg.stream] + sg.dn0, ctx->d_out + out_off[sg.stream] + sg.dn0, sg.dn1 - sg.dn0, cudaMemcpyDeviceToHost, ctx->s_out);
+        ok(cudaMemcpyAsync(outputs[sg.stream] + sg.dn0, ctx->d_out + out_off[sg.stream] + sg.dn0, sg.dn1 - sg.dn0, cudaMemcpyDeviceToHost, ctx->s_out));
     }
   }
-  cudaStreamSynchronize(ctx->s_in);
-  cudaStreamSynchronize(ctx->s_out);
+  // drain all three streams whatever happened (nothing may still be writing into the caller's buffers on return)
+  ok(cudaStreamSynchronize(ctx->s_in));
+  ok(cudaStreamSynchronize(ctx->stream));
+  ok(cudaStreamSynchronize(ctx->s_out));
+  if (pipe_err != cudaSuccess) return fail(ctx, "host-pointer pipeline", pipe_err);
   plan->last_stream = ctx->stream;
   if (!rc) rc = bgx_plan_finish(ctx, plan, nullptr);
   if (!rc) {
     double sum = 0;
     for (uint32_t g = 0; g < G; ++g) {
       float ms = 0;
-      if (cudaEventElapsedTime(&ms, ev[3 * g + 1], ev[3 * g + 2]) == cudaSuccess) sum += ms;
+      BGX_CUDA(ctx, cudaEventElapsedTime(&ms, ev[3 * g + 1], ev[3 * g + 2]));
+      sum += ms;
     }
     if (kernel_ms) *kernel_ms += sum;
     for (uint32_t i = 0; i < n; ++i) output_sizes[i] = info[i].uncompressed_size;
   }
-  for (auto& e : ev) cudaEventDestroy(e);
-  cudaEventDestroy(ev_start);
-  bgx_plan_destroy(plan);
   return rc;
 }
 

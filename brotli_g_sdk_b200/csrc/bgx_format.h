@@ -119,8 +119,14 @@ BGX_HD int parse_stream_header(const uint8_t* s, StreamInfo* out) {
   out->page_size = kMinPageSize << (w1 & 3u);
   out->last_page_size = (w1 >> 2) & 0x3ffffu;
   out->preconditioned = (w1 >> 20) & 1u;
-  out->uncompressed_size =
-      out->num_pages * out->page_size - (out->last_page_size ? out->page_size - out->last_page_size : 0u);
+  // The API carries sizes in 32 bits (BrotligDecoder.h:32-33), the header can describe up to 65535 x 128 KiB = 8 GiB:
+  // the reference lets that product wrap (DataStream.h:60-64); a stream whose size does not fit is rejected here, and
+  // so is a last page larger than a page.
+  const uint64_t full = (uint64_t)out->num_pages * out->page_size;
+  if (out->last_page_size > out->page_size) return kErrCorruptStream;
+  const uint64_t size = full - (out->last_page_size && out->num_pages ? out->page_size - out->last_page_size : 0u);
+  if (size > 0xffffffffull) return kErrCorruptStream;
+  out->uncompressed_size = (uint32_t)size;
   out->header_bytes = kStreamHeaderBytes + (out->preconditioned ? kPreconHeaderBytes : 0u);
   return kOk;
 }
@@ -153,7 +159,9 @@ struct PreconLayout {
 
 // Mirrors BrotligDataconditionParams::Initialize (BrotligDataConditioner.h:92-237) for the decode
 // side, where width/height/pitch of mip 0 come from the PreconditionHeader (+1 applied by caller,
-// BrotligDecoder.cpp:470-476). Returns false exactly when the reference's Initialize does.
+// BrotligDecoder.cpp:470-476). Returns false when the reference's Initialize does, and -- unlike the reference, which
+// trusts these header fields and then scatters outside the texture -- when a pitch is smaller than a row of blocks,
+// when the blocks do not fit the output, or when the sizes overflow 32 bits.
 inline bool precon_layout_init(PreconLayout* L, uint32_t format, uint32_t width_blocks, uint32_t height_blocks,
                                uint32_t pitch_bytes, uint32_t num_mips, bool swizzle, bool pitch_aligned,
                                uint32_t out_size) {
@@ -182,7 +190,7 @@ inline bool precon_layout_init(PreconLayout* L, uint32_t format, uint32_t width_
   L->num_mips = num_mips;
   L->width_blocks[0] = width_blocks;
   L->height_blocks[0] = height_blocks;
-  L->total_blocks = L->num_blocks[0] = width_blocks * height_blocks;
+  L->total_blocks = L->num_blocks[0] = width_blocks * height_blocks;   // (15 + 15 bits)
   auto round_up = [](uint32_t n, uint32_t m) { return ((n + m - 1) / m) * m; };
   L->pitch_bytes[0] = pitch_bytes ? pitch_bytes
                                   : (pitch_aligned ? round_up(width_blocks * L->block_bytes, 256u)
@@ -197,7 +205,10 @@ inline bool precon_layout_init(PreconLayout* L, uint32_t format, uint32_t width_
                                           : L->width_blocks[mip] * L->block_bytes;
       L->total_blocks += L->num_blocks[mip];
     }
-    L->mip_off_bytes[mip] = L->mip_off_bytes[mip - 1] + L->pitch_bytes[mip - 1] * L->height_blocks[mip - 1];
+    if (L->pitch_bytes[mip - 1] < L->width_blocks[mip - 1] * L->block_bytes) return false;   // rows would overlap / leave the texture
+    const uint64_t end = (uint64_t)L->mip_off_bytes[mip - 1] + (uint64_t)L->pitch_bytes[mip - 1] * L->height_blocks[mip - 1];
+    if (end > out_size) return false;
+    L->mip_off_bytes[mip] = (uint32_t)end;
     L->mip_off_blocks[mip] = L->mip_off_blocks[mip - 1] + L->num_blocks[mip - 1];
     wpx /= 2;
     hpx /= 2;
@@ -205,6 +216,7 @@ inline bool precon_layout_init(PreconLayout* L, uint32_t format, uint32_t width_
   // The reference bails out here with isInitialized=false but keeps decoding with whatever was
   // filled in so far (sub_off / sub_stream_off still zero). We report it; callers decide.
   if (L->mip_off_bytes[num_mips] != out_size) return false;
+  if ((uint64_t)L->total_blocks * L->block_bytes > out_size) return false;   // the conditioned planes hold out_size bytes
   for (uint32_t sub = 1; sub <= L->num_sub; ++sub) {
     if (sub < L->num_sub) L->sub_off[sub] = L->sub_off[sub - 1] + L->sub_size[sub - 1];
     L->sub_stream_off[sub] = L->sub_stream_off[sub - 1];

@@ -42,9 +42,11 @@
 #include <cuda_runtime.h>
 #define BGX_DEV __device__ __forceinline__
 #define BGX_DEV_NOINLINE __device__ __forceinline__
+#define BGX_COLD __device__ __noinline__     // rare paths: out of line, so that the round loops stay small
 #else
 #define BGX_DEV inline
 #define BGX_DEV_NOINLINE inline
+#define BGX_COLD inline
 #endif
 
 #ifndef BGX_WAIT_SLEEP_NS
@@ -320,6 +322,17 @@ BGX_DEV uint32_t br_read(BitRd& r, const PageIn& in, uint32_t n) {   // n <= 32
   return v;
 }
 
+// Rare wide fields (24-bit length extras, distance extras that do not fit the peek), out of line: skips `skip` bits,
+// then reads n1 and n2 bits. The caller passes copies of its reader state and takes them back.
+struct ColdBits { BitRd r; PageIn in; uint32_t second; };
+BGX_COLD uint32_t cold_read_fields(ColdBits* c, uint32_t skip, uint32_t n1, uint32_t n2) {
+  br_skip(c->r, c->in, skip);
+  const uint32_t first = br_read(c->r, c->in, n1);
+  c->second = br_read(c->r, c->in, n2);
+  return first;
+}
+BGX_COLD uint32_t cold_udiv(uint32_t a, uint32_t b) { return a / b; }
+
 BGX_DEV uint32_t warp_index() {
 #ifdef BGX_EMULATED
   return (uint32_t)wemu::warp_id();
@@ -366,6 +379,7 @@ BGX_DEV uint32_t huff_decode(const uint16_t* lut, const HuffAux& aux, const Sort
   }
   const uint32_t msb = __brev(peek) >> 17;   // first 15 stream bits as an MSB-first number
   uint32_t L = BITS + 1;
+#pragma unroll 1
   while (L < 15u && msb >= aux.limit[L]) ++L;
   len = L;
   uint32_t idx = (uint16_t)(aux.base[L] + (msb >> (15u - L)));
@@ -626,6 +640,11 @@ BGX_DEV void mbar_init(saddr_t a, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
 #endif
 }
+BGX_DEV void mbar_inval(saddr_t a) {
+#ifndef BGX_EMULATED
+  asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(a) : "memory");
+#endif
+}
 BGX_DEV void mbar_init_fence() {
 #ifndef BGX_EMULATED
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -642,23 +661,26 @@ BGX_DEV void mbar_wait(saddr_t a, uint32_t parity) {
 #ifdef BGX_EMULATED
   wemu::mbar_wait(reinterpret_cast<uint64_t*>(a), parity);
 #else
-  // try_wait suspends the warp for a short, hardware-defined time before it reports "not yet", so this loop is
-  // not a busy spin. An extra nanosleep back-off (BGX_WAIT_SLEEP_NS > 0) was measured: it changes nothing when
-  // the SM is full and costs single-page latency (each hand-over may then wait out the sleep), so it is off.
+  // try_wait suspends the warp until the phase completes or a time limit passes. Without the optional time-limit
+  // operand that limit is short: the waiting side of a round then issued ~200 instructions of this loop per round
+  // (17 % of all issued instructions of the kernel). With a long limit the warp sleeps until the arrive wakes it.
   uint32_t done;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(a), "r"(parity) : "memory");
-  while (!done) {
-#if BGX_WAIT_SLEEP_NS > 0
-    __nanosleep(BGX_WAIT_SLEEP_NS);
+#ifndef BGX_WAIT_HINT_NS
+#define BGX_WAIT_HINT_NS 0x989680
 #endif
+  do {
+#if BGX_WAIT_HINT_NS > 0
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(a), "r"(parity), "r"((uint32_t)BGX_WAIT_HINT_NS) : "memory");
+#else
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(a), "r"(parity) : "memory");
-  }
+#endif
+  } while (!done);
 #endif
 }
 // the whole warp signals: its earlier shared-memory accesses are ordered before the elected lane's arrive
@@ -669,9 +691,123 @@ BGX_DEV void warp_arrive(saddr_t a, uint32_t lane) {
 BGX_DEV uint32_t ld_volatile_u32(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
 
 // ------------------------------------------------------------------------------------- PRODUCER
+// Hand-over state of the producer. In the round loop it lives in registers (every member function is inlined); the
+// rare long-run path (slow_round, out of line so that it stays out of the instruction cache) works on a copy.
+struct ProdCtx {
+  WarpSmem* sm;
+  saddr_t full_a, empty_a;
+  uint32_t lane;
+  uint32_t rnd;            // rounds published so far
+  uint32_t synced;         // empty[] phases taken so far: rounds < synced are known to be consumed
+  uint32_t lit_tail;       // literals decoded so far
+  uint32_t lit_head_p;     // literals that the rounds published so far consume
+
+  // waits until slot rnd % kQ is free
+  BGX_DEV void acquire_slot() {
+    while (synced + kQ <= rnd) {   // the slot still holds round rnd - kQ: wait until the consumer is done with it
+      mbar_wait(empty_a + 8u * (synced & (kQ - 1u)), (synced / kQ) & 1u);
+      ++synced;
+    }
+  }
+  // the literal ring must hold `newlits` more literals next to those of every round the consumer may still be
+  // working on (rounds >= synced): takes more empty[] phases while that helps; false if they cannot fit at all
+  BGX_DEV bool wait_lit_room(uint32_t newlits) {
+    uint32_t head_known = synced == rnd ? lit_head_p : sm->ctl.phead[synced & (kQ - 1u)];
+    bool fits = (lit_tail - head_known) + newlits <= kLitQ;
+    while (!fits && synced < rnd) {
+      mbar_wait(empty_a + 8u * (synced & (kQ - 1u)), (synced / kQ) & 1u);
+      ++synced;
+      head_known = synced == rnd ? lit_head_p : sm->ctl.phead[synced & (kQ - 1u)];
+      fits = (lit_tail - head_known) + newlits <= kLitQ;
+    }
+    return fits;
+  }
+  // publishes round `rnd`: final distance; inclusive sums (output | literals << 16) | flags
+  BGX_DEV void publish(uint32_t dxv, uint32_t pkv) {
+    const uint32_t q = rnd & (kQ - 1u);
+    if (lane == 0) sm->ctl.phead[q] = lit_head_p;   // literal head at the start of this round
+    sm->rb[q].cmd[lane] = make_uint2(dxv, pkv);
+    warp_arrive(full_a + 8u * q, lane);
+    ++rnd;
+  }
+  // ends the page with an error: the slot of round `rnd` (free: every caller has acquired it) carries the abort flag
+  BGX_DEV void publish_abort(uint32_t err) {
+    const uint32_t q = rnd & (kQ - 1u);
+    if (err && lane == 0) sm->ctl.err = err;
+    sm->rb[q].cmd[lane] = make_uint2(0u, kPkAbort);
+    warp_arrive(full_a + 8u * q, lane);
+  }
+};
+
+struct SlowRound {           // what slow_round needs of the producer's registers (copied in and out around the call)
+  ProdCtx pc;
+  BitRd rd;
+  PageIn in;
+  uint32_t ins, cpy, mine, dx, pdone;
+};
+
+// A round with long runs (more output than the ring path takes at once, or more literals than the literal ring
+// holds) is handed over as a sequence of VIRTUAL rounds that each fit: a virtual round takes as many whole commands
+// as fit, in order, or -- when the next command alone is too big -- a piece of it (first <= kSplitLits of its literals
+// at a time, then <= kRoundMax bytes of its copy at a time; a copy split in two is the same byte-serial copy,
+// PageDecoder.cpp:222-232). The consumer sees ordinary rounds in which the other lanes carry empty commands; the
+// round's literals are decoded row by row (32 at a time, all lanes) as the virtual rounds need them.
+// Returns false when the page was aborted (the abort round is then published).
+BGX_COLD bool slow_round(SlowRound* a) {
+  ProdCtx pc = a->pc;          // (local copies: the argument block lives in local memory)
+  BitRd rd = a->rd;
+  PageIn in = a->in;
+  const uint32_t dx = a->dx;
+  const bool pdone = a->pdone != 0;
+  struct WriteBack { SlowRound* a; ProdCtx& pc; BitRd& rd; PageIn& in; BGX_DEV ~WriteBack() { a->pc = pc; a->rd = rd; a->in = in; } } wb{a, pc, rd, in};
+  const uint32_t lane = pc.lane;
+  uint32_t rem_ins = a->ins, rem_cpy = a->cpy;   // what is left of this lane's command
+  uint32_t s_mine = a->mine;                     // literals this lane still has to decode in this round
+  bool first = true;
+  for (;;) {
+    const uint32_t work = __ballot_sync(kFull, (rem_ins | rem_cpy) != 0u);
+    if (!first) pc.acquire_slot();
+    first = false;
+    const uint32_t a0 = work ? (uint32_t)(__ffs((int)work) - 1) : 32u;   // first command with something left
+    uint32_t v_ins = rem_ins, v_cpy = rem_cpy;
+    if (lane == a0) {                        // the leading command may have to be clipped
+      if (v_ins > kSplitLits) { v_ins = kSplitLits; v_cpy = 0; }
+      else if (v_cpy > kRoundMax - v_ins) v_cpy = kRoundMax - v_ins;
+    }
+    const bool clipped = __ballot_sync(kFull, lane == a0 && (v_ins != rem_ins || v_cpy != rem_cpy)) != 0u;
+    const uint64_t vincl = warp_incl_scan64(((uint64_t)(v_ins + v_cpy) << 32) | v_ins, lane);
+    const bool ok = (uint32_t)(vincl >> 32) <= kRoundMax && (uint32_t)vincl <= kSplitLits;
+    const uint32_t notok = ~__ballot_sync(kFull, ok) & ~(0xffffffffu >> (31u - (a0 & 31u)));   // lanes > a0 that do not fit
+    const uint32_t b0 = a0 >= 32u ? 32u : clipped ? a0 + 1u : (notok ? (uint32_t)(__ffs((int)notok) - 1) : 32u);
+    if (lane >= b0) { v_ins = 0; v_cpy = 0; }
+    const uint64_t vtot = __shfl_sync(kFull, vincl, (int)((b0 ? b0 : 1u) - 1u));   // sums over the taken commands
+    const uint64_t vpk = lane < b0 ? vincl : vtot;
+    const uint32_t vr_ins = (uint32_t)vtot;
+    rem_ins -= v_ins;
+    rem_cpy -= v_cpy;
+    const bool last_virtual = __ballot_sync(kFull, (rem_ins | rem_cpy) != 0u) == 0u;
+    // literals: whole rows until the virtual round is covered; everything the round still carries with the last one
+    const uint32_t have = pc.lit_tail - pc.lit_head_p;
+    const uint32_t want = vr_ins > have ? vr_ins - have : 0u;
+    const uint32_t rows = (want + 31u) >> 5;
+    const uint32_t c = last_virtual ? s_mine : (s_mine < rows ? s_mine : rows);
+    const uint32_t total = __reduce_add_sync(kFull, c);
+    if (have + total < vr_ins || !pc.wait_lit_room(total)) {   // the stream does not carry the literals it inserts
+      pc.publish_abort(kPageErrLiterals);
+      return false;
+    }
+    decode_literals(pc.sm, rd, in, pc.lit_tail, c, lane);
+    s_mine -= c;
+    pc.publish(dx, (uint32_t)(vpk >> 32) | ((uint32_t)vpk << 16) | ((last_virtual && pdone) ? kPkLast : 0u));
+    pc.lit_tail += total;
+    pc.lit_head_p += vr_ins;
+    if (last_virtual) return true;
+  }
+}
+
 BGX_DEV void producer_warp(const PageJob& job, WarpSmem* sm) {
-  const uint32_t lane = lane_id();
-  const uint32_t lt_mask = (1u << lane) - 1u;
+  const uint32_t lane = pinned(lane_id());
+  const uint32_t lt_mask = pinned((1u << lane) - 1u);
   PageCtl* ctl = &sm->ctl;
   const uint32_t out_size = job.out_size;
 
@@ -729,54 +865,25 @@ BGX_DEV void producer_warp(const PageJob& job, WarpSmem* sm) {
   if (!terr) terr = load_table<kLitLutBits>(sm, rd, in, bgx::kNumLitSymbols, sm->lut_lit, sm->aux[2], sm->sorted_lit, lane);
   __syncwarp();
 
-  const saddr_t full_a = saddr(sm->mbar), empty_a = full_a + 8u * kQ;
-  uint32_t rnd = 0;            // rounds published so far
-  uint32_t synced = 0;         // empty[] phases taken so far: rounds < synced are known to be consumed
-  uint32_t lit_tail = 0;       // literals decoded so far
-  uint32_t lit_head_p = 0;     // literals that the rounds published so far consume
+  ProdCtx pc;
+  pc.sm = sm;
+  pc.full_a = saddr_pinned(sm->mbar);
+  pc.empty_a = pc.full_a + 8u * kQ;
+  pc.lane = lane;
+  pc.rnd = 0;
+  pc.synced = 0;
+  pc.lit_tail = 0;
+  pc.lit_head_p = 0;
   uint32_t ringv = (0x100f0b04u >> (8u * (lane & 3u))) & 0xffu;   // distance ring {4, 11, 15, 16} (PageDecoder.cpp:150-153): lane l keeps entry l & 3
   bool pdone = false;
   uint32_t pos_p = 0;          // bytes the rounds published so far produce
-  // ends the page with an error: the slot of round `rnd` (free: every caller has acquired it) carries the abort flag
-  auto publish_abort = [&](uint32_t err) {
-    const uint32_t q = rnd & (kQ - 1u);
-    if (err && lane == 0) ctl->err = err;
-    sm->rb[q].cmd[lane] = make_uint2(0u, kPkAbort);
-    warp_arrive(full_a + 8u * q, lane);
-  };
-  // waits until slot rnd % kQ is free
-  auto acquire_slot = [&]() {
-    while (synced + kQ <= rnd) {   // the slot still holds round rnd - kQ: wait until the consumer is done with it
-      mbar_wait(empty_a + 8u * (synced & (kQ - 1u)), (synced / kQ) & 1u);
-      ++synced;
-    }
-  };
-  // the literal ring must hold `newlits` more literals next to those of every round the consumer may still be
-  // working on (rounds >= synced): takes more empty[] phases while that helps; false if they cannot fit at all
-  auto wait_lit_room = [&](uint32_t newlits) -> bool {
-    uint32_t head_known = synced == rnd ? lit_head_p : ctl->phead[synced & (kQ - 1u)];
-    bool fits = (lit_tail - head_known) + newlits <= kLitQ;
-    while (!fits && synced < rnd) {
-      mbar_wait(empty_a + 8u * (synced & (kQ - 1u)), (synced / kQ) & 1u);
-      ++synced;
-      head_known = synced == rnd ? lit_head_p : ctl->phead[synced & (kQ - 1u)];
-      fits = (lit_tail - head_known) + newlits <= kLitQ;
-    }
-    return fits;
-  };
-  auto publish = [&](uint32_t dxv, uint32_t pkv, uint32_t flags) {
-    const uint32_t q = rnd & (kQ - 1u);
-    sm->rb[q].cmd[lane] = make_uint2(dxv, pkv | flags);   // final distance; inclusive sums: output | literals << 16
-    warp_arrive(full_a + 8u * q, lane);
-    ++rnd;
-  };
   if (terr) {   // a malformed prefix-code description: the page ends here
-    publish_abort(terr);
+    pc.publish_abort(terr);
     return;
   }
   const uint32_t postfix_mask = (1u << npostfix) - 1u;
   for (;;) {
-    acquire_slot();
+    pc.acquire_slot();
     br_topup1(rd, in);
     // ---- one command per lane, speculatively: the lanes behind the sentinel consume nothing. Straight-line code
     //      with two window refills (after the insert&copy part and after the distance part); only 24-bit extra
@@ -796,10 +903,12 @@ BGX_DEV void producer_warp(const PageJob& job, WarpSmem* sm) {
     const uint32_t nbi = ei >> 16, nbc = ec >> 16;
     uint32_t adv = len + nbi + nbc;
     uint32_t ins = ei & 0xffffu, cpy = ec & 0xffffu;
-    if (act && adv > 32u) {           // 24-bit extras: field by field
-      br_skip(rd, in, len);
-      ins += br_read(rd, in, nbi);
-      cpy += br_read(rd, in, nbc);
+    if (act && adv > 32u) {           // 24-bit extras: field by field (rare, out of line)
+      ColdBits cb;
+      cb.r = rd; cb.in = in;
+      ins += cold_read_fields(&cb, len, nbi, nbc);
+      cpy += cb.second;
+      rd = cb.r;
       adv = 0;
     } else {                          // symbol + both extra-bit fields out of the one 32-bit peek
       ins += shr32(pk, len) & low_mask(nbi);
@@ -828,9 +937,11 @@ BGX_DEV void producer_warp(const PageJob& job, WarpSmem* sm) {
           if (len2 + nb <= 32u) {
             extra = shr32(pk2, len2) & low_mask(nb);
             adv2 = len2 + nb;
-          } else {
-            br_skip(rd, in, len2);
-            extra = br_read(rd, in, nb);
+          } else {                    // (rare, out of line)
+            ColdBits cb;
+            cb.r = rd; cb.in = in;
+            extra = cold_read_fields(&cb, len2, nb, 0u);
+            rd = cb.r;
           }
           const uint32_t h = v >> npostfix, lo = v & postfix_mask;
           const uint32_t dexp = (((((2u + (h & 1u)) << nb) - 4u + extra) << npostfix) + lo + ndirect + 1u) & 0x7fffffffu;
@@ -870,11 +981,11 @@ BGX_DEV void producer_warp(const PageJob& job, WarpSmem* sm) {
       const uint32_t src_lane = from_carry ? 0u : (uint32_t)(31 - __clz((int)b));
       const uint32_t cslot = slot - (from_carry ? npush_below : 0u);
       const uint32_t carry_val = __shfl_sync(kFull, ringv, (int)cslot);
-#ifdef BGX_RING_PJ
-      // EXPERIMENT (off by default, not yet measured on the GPU): pointer jumping instead of relaxation. Every
-      // unresolved command holds (source lane, accumulated offset); a step either picks up the source's final
-      // value or adopts the source's own source, so a chain of length n resolves in ceil(log2 n) + 1 steps instead
-      // of n (record-like data averages 5.6 relaxation steps per round).
+#ifndef BGX_RING_RELAX
+      // Pointer jumping: every unresolved command holds (source lane, accumulated offset); a step either picks up the
+      // source's final value or adopts the source's own source, so a chain of length n resolves in ceil(log2 n) + 1
+      // steps instead of the n of a plain relaxation (-DBGX_RING_RELAX; record-like data averages 5.6 relaxation
+      // steps per round, 2.9 jumps: structured binary 182 -> 192 GB/s).
       if (unresolved && from_carry) {
         dist = (uint32_t)((int32_t)carry_val + delta);
         unresolved = false;
@@ -943,9 +1054,9 @@ BGX_DEV void producer_warp(const PageJob& job, WarpSmem* sm) {
     }
     (void)incl_ins;
     // ---- literals of this round (PageDecoder.cpp:196-206)
-    const uint32_t avail = lit_tail - lit_head_p;     // decoded ahead of need in earlier rounds (< 32)
+    const uint32_t avail = pc.lit_tail - pc.lit_head_p;     // decoded ahead of need in earlier rounds (< 32)
     const uint32_t need = round_ins > avail ? round_ins - avail : 0u;
-    const uint32_t mult = n ? (n == 32u ? (need + 31u) >> 5 : (need + n - 1u) / n) : 0u;
+    const uint32_t mult = n ? (n == 32u ? (need + 31u) >> 5 : cold_udiv(need + n - 1u, n)) : 0u;   // (n < 32: last round only)
     const uint32_t rl = n * mult;                     // literals the stream carries for this round
     uint32_t mine = rl > lane ? (rl - lane + 31u) >> 5 : 0u;   // literal indices lit_tail + j*32 + lane
     {
@@ -954,84 +1065,41 @@ BGX_DEV void producer_warp(const PageJob& job, WarpSmem* sm) {
       const uint32_t o_cpy_page = pos_p + incl_tot - cpy;   // page offset where this command's copy lands
       const uint32_t baddist = __ballot_sync(kFull, cpy != 0u && (dx == 0u || dx > o_cpy_page));
       pos_p += round_out;
-      if (round_out > out_size || pos_p > out_size) { publish_abort(kPageErrOverrun); break; }
-      if (baddist) { publish_abort(kPageErrDistance); break; }
+      if (round_out > out_size || pos_p > out_size) { pc.publish_abort(kPageErrOverrun); break; }
+      if (baddist) { pc.publish_abort(kPageErrDistance); break; }
     }
     bool fast = !big && round_out <= kRoundMax && rl <= kLitQ;
-    if (fast) fast = wait_lit_room(rl);
+    if (fast) fast = pc.wait_lit_room(rl);
     BGX_STAT(emu_stats().rounds++; emu_stats().lits += rl; if (!fast) emu_stats().slow_rounds++);
     if (fast) {
-      if (lane == 0) ctl->phead[rnd & (kQ - 1u)] = lit_head_p;   // literal head at the start of this round
-      decode_literals(sm, rd, in, lit_tail, mine, lane);
-      lit_tail += rl;
-      lit_head_p += round_ins;
-      publish(dx, pkv, pdone ? kPkLast : 0u);
-    } else {
-      // ---- a round with long runs (more output than the ring path takes at once, or more literals than the
-      //      literal ring holds) is handed over as a sequence of VIRTUAL rounds that each fit: a virtual round
-      //      takes as many whole commands as fit, in order, or -- when the next command alone is too big -- a
-      //      piece of it (first <= kSplitLits of its literals at a time, then <= kRoundMax bytes of its copy at a
-      //      time; a copy split in two is the same byte-serial copy, PageDecoder.cpp:222-232). The consumer sees
-      //      ordinary rounds in which the other lanes carry empty commands; the round's literals are decoded
-      //      row by row (32 at a time, all lanes) as the virtual rounds need them.
-      uint32_t rem_ins = ins, rem_cpy = cpy;   // what is left of this lane's command
-      uint32_t s_mine = mine;                  // literals this lane still has to decode in this round
-      bool first = true, aborted = false;
-      for (;;) {
-        const uint32_t work = __ballot_sync(kFull, (rem_ins | rem_cpy) != 0u);
-        if (!first) acquire_slot();
-        first = false;
-        const uint32_t qv = rnd & (kQ - 1u);
-        const uint32_t a0 = work ? (uint32_t)(__ffs((int)work) - 1) : 32u;   // first command with something left
-        uint32_t v_ins = rem_ins, v_cpy = rem_cpy;
-        if (lane == a0) {                        // the leading command may have to be clipped
-          if (v_ins > kSplitLits) { v_ins = kSplitLits; v_cpy = 0; }
-          else if (v_cpy > kRoundMax - v_ins) v_cpy = kRoundMax - v_ins;
-        }
-        const bool clipped = __ballot_sync(kFull, lane == a0 && (v_ins != rem_ins || v_cpy != rem_cpy)) != 0u;
-        const uint64_t vincl = warp_incl_scan64(((uint64_t)(v_ins + v_cpy) << 32) | v_ins, lane);
-        const bool ok = (uint32_t)(vincl >> 32) <= kRoundMax && (uint32_t)vincl <= kSplitLits;
-        const uint32_t notok = ~__ballot_sync(kFull, ok) & ~(0xffffffffu >> (31u - (a0 & 31u)));   // lanes > a0 that do not fit
-        const uint32_t b0 = a0 >= 32u ? 32u : clipped ? a0 + 1u : (notok ? (uint32_t)(__ffs((int)notok) - 1) : 32u);
-        if (lane >= b0) { v_ins = 0; v_cpy = 0; }
-        const uint64_t vtot = __shfl_sync(kFull, vincl, (int)((b0 ? b0 : 1u) - 1u));   // sums over the taken commands
-        const uint64_t vpk = lane < b0 ? vincl : vtot;
-        const uint32_t vr_ins = (uint32_t)vtot;
-        rem_ins -= v_ins;
-        rem_cpy -= v_cpy;
-        const bool last_virtual = __ballot_sync(kFull, (rem_ins | rem_cpy) != 0u) == 0u;
-        // literals: whole rows until the virtual round is covered; everything the round still carries with the last one
-        const uint32_t have = lit_tail - lit_head_p;
-        const uint32_t want = vr_ins > have ? vr_ins - have : 0u;
-        const uint32_t rows = (want + 31u) >> 5;
-        const uint32_t c = last_virtual ? s_mine : (s_mine < rows ? s_mine : rows);
-        const uint32_t total = __reduce_add_sync(kFull, c);
-        if (have + total < vr_ins || !wait_lit_room(total)) {   // the stream does not carry the literals it inserts
-          publish_abort(kPageErrLiterals);
-          aborted = true;
-          break;
-        }
-        if (lane == 0) ctl->phead[qv] = lit_head_p;
-        decode_literals(sm, rd, in, lit_tail, c, lane);
-        s_mine -= c;
-        lit_tail += total;
-        lit_head_p += vr_ins;
-        publish(dx, (uint32_t)(vpk >> 32) | ((uint32_t)vpk << 16), (last_virtual && pdone) ? kPkLast : 0u);
-        if (last_virtual) break;
-      }
-      if (aborted) break;
+      decode_literals(sm, rd, in, pc.lit_tail, mine, lane);
+      pc.publish(dx, pkv | (pdone ? kPkLast : 0u));
+      pc.lit_tail += rl;
+      pc.lit_head_p += round_ins;
+    } else {   // a round with long runs: virtual rounds (slow_round)
+      SlowRound a;
+      a.pc = pc; a.rd = rd; a.in = in;
+      a.ins = ins; a.cpy = cpy; a.mine = mine; a.dx = dx; a.pdone = pdone ? 1u : 0u;
+      const bool ok = slow_round(&a);
+      pc = a.pc; rd = a.rd; in = a.in;
+      if (!ok) break;
     }
     if (pdone) break;
   }
 }
 
 // ------------------------------------------------------------------------------------- CONSUMER
+// rare paths of the consumer, out of line
+BGX_COLD void cold_flush_bytes(const WarpSmem* sm, uint8_t* out, uint32_t from, uint32_t to, uint32_t zero_to, uint32_t lane) {
+  for (uint32_t p = from + lane; p < to; p += 32) out[p] = sm->ring[p & (kRing - 1)];
+  for (uint32_t z = to + lane; z < zero_to; z += 32) out[z] = 0;
+}
 // Positions are kept in "v-space": v = page offset + skew, skew = (output address & 15), so that v % 16 == 0 is
 // a 16-byte boundary of global memory whatever the caller's pointer is (word loads of far matches and the vector
 // flush are then always aligned). Every round the consumer sees was validated by the producer (it fits the page,
 // every match starts inside the page), so nothing here can fail.
 #ifndef BGX_PIECE_BATCH
-#define BGX_PIECE_BATCH 4
+#define BGX_PIECE_BATCH 2
 #endif
 constexpr int kPieceBatch = BGX_PIECE_BATCH;   // chunks (of 32 pieces) whose source loads are issued back to back
 
@@ -1168,18 +1236,10 @@ BGX_DEV void consumer_warp(const PageJob& job, WarpSmem* sm) {
           const uint32_t m = meta[u];
           const uint32_t v = __funnelshift_r(w0[u], w1[u], m);          // (shift = low five bits = 8 * (source & 3))
           const uint32_t dd = m >> 8;                                    // ring offset of the piece's first byte
-          const saddr_t a = ring_a + dd;
-          if (dd <= kRing - 4u) {                                        // (all but 3 in 2048 pieces: no wrap inside the piece)
-            if (m & (7u << 5)) sts_u8(a, v);
-            if (m & (6u << 5)) sts_u8(a + 1u, v >> 8);                   // rem >= 2
-            if ((m & (7u << 5)) >= (3u << 5)) sts_u8(a + 2u, v >> 16);
-            if (m & (4u << 5)) sts_u8(a + 3u, v >> 24);                  // rem == 4
-          } else {
-            if (m & (7u << 5)) sts_u8(a, v);
-            if (m & (6u << 5)) sts_u8(ring_at(ring_a, dd + 1u), v >> 8);
-            if ((m & (7u << 5)) >= (3u << 5)) sts_u8(ring_at(ring_a, dd + 2u), v >> 16);
-            if (m & (4u << 5)) sts_u8(ring_at(ring_a, dd + 3u), v >> 24);
-          }
+          if (m & (7u << 5)) sts_u8(ring_a + dd, v);
+          if (m & (6u << 5)) sts_u8(ring_at(ring_a, dd + 1u), v >> 8);   // rem >= 2
+          if ((m & (7u << 5)) >= (3u << 5)) sts_u8(ring_at(ring_a, dd + 2u), v >> 16);
+          if (m & (4u << 5)) sts_u8(ring_at(ring_a, dd + 3u), v >> 24);  // rem == 4
         }
       }
       __syncwarp();
@@ -1197,7 +1257,7 @@ BGX_DEV void consumer_warp(const PageJob& job, WarpSmem* sm) {
           BGX_STAT(emu_stats().wavefronts++; emu_stats().sum_max_cpy += n_k);
           if (n_k <= 32u && d_k >= n_k) {                                  // the usual case: one step, no overlap
             if (lane < n_k) sts_u8(ring_at(ring_a, o_k + lane), lds_u8(ring_at(ring_a, o_k - d_k + lane)));
-          } else {
+          } else {                                                         // long or overlapping
 #pragma unroll 1
             for (uint32_t j = lane; j < n_k; j += 32) {
               const uint32_t mj = j < d_k ? j : j % d_k;
@@ -1215,7 +1275,7 @@ BGX_DEV void consumer_warp(const PageJob& job, WarpSmem* sm) {
     if (pos - flushed >= kFlushChunk) {
       if (flushed & 15u) {   // page start of an unaligned output buffer
         const uint32_t to = (flushed + 15u) & ~15u;
-        flush_bytes(sm, outb, flushed, to, lane);
+        cold_flush_bytes(sm, outb, flushed, to, to, lane);
         flushed = to;
       }
       while (pos - flushed >= kFlushChunk) {
@@ -1227,21 +1287,25 @@ BGX_DEV void consumer_warp(const PageJob& job, WarpSmem* sm) {
     }
     if (cw.y & kPkLast) {
       // ---- last round: whatever is still only in the ring, then zero-fill (the reference memsets the page first)
-      flush_bytes(sm, outb, flushed, pos, lane);
-      for (uint32_t z = pos + lane; z < end_v; z += 32) outb[z] = 0;
+      cold_flush_bytes(sm, outb, flushed, pos, end_v, lane);
       break;
     }
   }
 }
 
 // All threads of the CTA call this with identical arguments.
-BGX_DEV_NOINLINE PageResult decode_page_cta(const PageJob& job, WarpSmem* sm) {
+BGX_DEV_NOINLINE PageResult decode_page_cta(const PageJob& job, WarpSmem* sm, bool first_page) {
 #ifndef BGX_EMULATED
   __builtin_assume(__isGlobal(job.out));
   __builtin_assume(__isGlobal(job.in));
 #endif
   if (warp_index() == 0 && lane_id() == 0) {
-    for (uint32_t i = 0; i < 2u * kQ; ++i) mbar_init(saddr(&sm->mbar[i]), 1u);
+    // (the CTA is persistent: from its second page on the words hold the previous page's barriers, possibly mid-phase
+    //  after an abort -- invalidate them before they are initialised again)
+    for (uint32_t i = 0; i < 2u * kQ; ++i) {
+      if (!first_page) mbar_inval(saddr(&sm->mbar[i]));
+      mbar_init(saddr(&sm->mbar[i]), 1u);
+    }
     mbar_init_fence();
     sm->ctl.err = 0;
   }

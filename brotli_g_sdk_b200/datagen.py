@@ -47,19 +47,19 @@ def text_like(n: int, seed: int = SEED_CONFIG4) -> np.ndarray:
     wl = rng.integers(2, 11, size=vocab)
     letters = rng.choice(26, size=int(wl.sum()), p=_letter_p()).astype(np.uint8) + 97
     starts = np.concatenate([[0], np.cumsum(wl)[:-1]])
-    words = [letters[s:s + l].tobytes() for s, l in zip(starts, wl)]
     ranks = rng.zipf(1.25, size=n // 4 + 16) % vocab
     seps = rng.choice(np.frombuffer(b"     ,.\n", dtype=np.uint8), size=len(ranks))
-    parts = []
-    total = 0
-    for r, sp in zip(ranks.tolist(), seps.tolist()):
-        w = words[r]
-        parts.append(w)
-        parts.append(bytes([sp]))
-        total += len(w) + 1
-        if total >= n:
-            break
-    out = np.frombuffer(b"".join(parts), dtype=np.uint8)
+    # token i = word ranks[i] + one separator; tokens are laid end to end until n bytes are covered (vectorised:
+    # every output byte looks up its token and its offset inside it)
+    tok_len = wl[ranks] + 1
+    ends = np.cumsum(tok_len)
+    k = min(int(np.searchsorted(ends, n)) + 1, len(ranks))
+    tok_len, ends = tok_len[:k], ends[:k]
+    total = int(ends[-1])
+    tok = np.repeat(np.arange(k, dtype=np.int64), tok_len)
+    off = np.arange(total, dtype=np.int64) - (ends - tok_len)[tok]
+    is_sep = off == wl[ranks[:k]][tok]
+    out = np.where(is_sep, seps[:k][tok], letters[np.minimum(starts[ranks[:k]][tok] + off, len(letters) - 1)]).astype(np.uint8)
     if len(out) < n:
         out = np.concatenate([out, np.full(n - len(out), 32, np.uint8)])
     return out[:n].copy()

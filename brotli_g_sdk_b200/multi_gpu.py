@@ -7,8 +7,9 @@ references, per-page prefix codes and distance ring: PageDecoder.cpp:126-153), s
   level 1  whole streams are assigned to ranks, size balanced: NO communication on the data path;
   level 2  one big stream (fewer streams than ranks): every rank decodes a contiguous page range
            [lo, hi) of it into its own output shard. The compressed bytes live on one rank, so the
-           stream is replicated with exactly ONE collective -- dist.broadcast over NCCL (NVLink 5 /
-           NVSwitch) -- and nothing else ever crosses the fabric; the output stays sharded.
+           stream is replicated with exactly ONE collective -- dist.broadcast of [size | stream] over
+           NCCL (NVLink 5 / NVSwitch) -- and nothing else ever crosses the fabric; the output stays
+           sharded. (Texture streams are not split: their owner decodes them whole.)
 
 The decode itself is always the CUDA path (BrotligDecoder.plan). `decode_fn` exists so that the
 plumbing (partitioning, broadcast, shard geometry) can be tested on CPU with the gloo backend.
@@ -65,40 +66,70 @@ class StreamGeometry:
         return n
 
 
-def decode_sharded_stream(stream_on_owner, owner: int, decode_fn: Callable, device=None, group=None):
-    """Level-2 decode of ONE stream across all ranks of `group`.
+SHARD_HEADER_BYTES = 16   # the broadcast buffer starts with the stream size (u64 LE) + 8 bytes of padding: payload stays 16-byte aligned
+
+
+def decode_sharded_stream(stream_on_owner, owner: int, decode_fn: Callable, device=None, group=None, capacity: int | None = None,
+                          timing: dict | None = None):
+    """Level-2 decode of ONE stream across all ranks of `group` (SURVEY.md section 8e).
 
     stream_on_owner: uint8 torch tensor holding the stream on rank `owner` (ignored elsewhere).
-    decode_fn(stream_tensor, geometry, lo, hi) -> output shard (bytes of pages [lo, hi)).
-    Returns (shard, (lo, hi), broadcast_bytes). Exactly one collective (the broadcast) is issued.
+    capacity:        an upper bound of the stream size that every rank knows (e.g. the largest stream the service
+                     accepts, or the size from the request metadata). The receive buffers are allocated from it and the
+                     stream size rides in the first 8 bytes of the broadcast buffer, so that EXACTLY ONE collective --
+                     the broadcast of [size | stream bytes] over NCCL (NVLink 5 / NVSwitch) -- is issued. Without it the
+                     size travels in a second, 8-byte control broadcast first.
+    decode_fn(buf, n, geometry, lo, hi) -> output shard (bytes of pages [lo, hi)); buf[:n] is the stream.
+    timing:          optional dict; receives "broadcast_ms" (CUDA events around the collective) on CUDA devices.
+    Returns (shard, (lo, hi), stream_bytes). Pre-conditioned (texture) streams are not split -- a page range of
+    a texture scatters into the whole texture -- so the owner decodes all pages and the other ranks get an empty shard.
     """
     import torch
     import torch.distributed as dist
 
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     dev = device if device is not None else (stream_on_owner.device if rank == owner else torch.device("cpu"))
-    # 1) size, then the bytes: a single broadcast carries [size (8 B) | stream] so there is one collective
+    if capacity is None:   # control-plane pre-broadcast of the size (8 bytes), then the data-path broadcast
+        meta = torch.tensor([int(stream_on_owner.numel()) if rank == owner else 0], dtype=torch.int64, device=dev)
+        dist.broadcast(meta, src=owner, group=group)
+        capacity = int(meta.item())
+    cap16 = ((capacity + 15) // 16) * 16
+    buf = torch.zeros(SHARD_HEADER_BYTES + cap16 + 64, dtype=torch.uint8, device=dev)
     if rank == owner:
         n = int(stream_on_owner.numel())
-        meta = torch.tensor([n], dtype=torch.int64, device=dev)
+        if n > capacity:
+            raise ValueError(f"stream of {n} bytes exceeds the agreed capacity {capacity}")
+        buf[:8] = torch.from_numpy(np.frombuffer(int(n).to_bytes(8, "little"), dtype=np.uint8).copy()).to(dev)
+        buf[SHARD_HEADER_BYTES: SHARD_HEADER_BYTES + n].copy_(stream_on_owner)
+    on_cuda = torch.device(dev).type == "cuda"
+    if on_cuda and timing is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    dist.broadcast(buf[: SHARD_HEADER_BYTES + cap16], src=owner, group=group)          # <- the one data-path collective
+    if on_cuda and timing is not None:
+        e1.record()
+        e1.synchronize()
+        timing["broadcast_ms"] = e0.elapsed_time(e1)
+        timing["broadcast_bytes"] = SHARD_HEADER_BYTES + cap16
+    head = bytes(buf[: SHARD_HEADER_BYTES + 16].cpu().numpy())
+    n = int.from_bytes(head[:8], "little")
+    geo = StreamGeometry.parse(head[SHARD_HEADER_BYTES:])
+    preconditioned = (int.from_bytes(head[SHARD_HEADER_BYTES + 4: SHARD_HEADER_BYTES + 8], "little") >> 20) & 1
+    if preconditioned:
+        lo, hi = (0, geo.num_pages) if rank == owner else (0, 0)
     else:
-        meta = torch.zeros(1, dtype=torch.int64, device=dev)
-    # the size is needed to allocate the receive buffer; it rides in an 8-byte pre-broadcast that is part of
-    # the control plane (not the data path). Callers that know the size can skip it via broadcast_stream().
-    dist.broadcast(meta, src=owner, group=group)
-    n = int(meta.item())
-    # receive buffer: 16-byte aligned (torch allocations are) and padded to the 16-byte staging granularity
-    buf = stream_on_owner if rank == owner else torch.zeros(((n + 15) // 16) * 16 + 64, dtype=torch.uint8, device=dev)
-    payload = buf[:n]
-    dist.broadcast(payload, src=owner, group=group)          # <- the one data-path collective
-    geo = StreamGeometry.parse(bytes(payload[:16].cpu().numpy()))
-    lo, hi = shard_pages(geo.num_pages, world)[rank]
-    shard = decode_fn(buf, n, geo, lo, hi)
+        lo, hi = shard_pages(geo.num_pages, world)[rank]
+    payload = buf[SHARD_HEADER_BYTES:]            # 16-byte aligned (torch allocations are 256-byte aligned)
+    if hi > lo:
+        shard = decode_fn(payload, n, geo, lo, hi)
+    else:
+        shard = torch.empty(0, dtype=torch.uint8, device=dev)
     return shard, (lo, hi), n
 
 
-def cuda_decode_fn(decoder):
-    """decode_fn for decode_sharded_stream backed by the CUDA plan interface."""
+def cuda_decode_fn(decoder, timing: dict | None = None):
+    """decode_fn for decode_sharded_stream backed by the CUDA plan interface. `timing`, if given, receives
+    "decode_ms": the CUDA-event duration of the launch."""
     import torch
 
     def fn(buf, n, geo: StreamGeometry, lo: int, hi: int):
@@ -116,8 +147,13 @@ def cuda_decode_fn(decoder):
         # run on a side stream ordered after whatever produced `buf` (e.g. the NCCL broadcast)
         side = torch.cuda.Stream(buf.device)
         side.wait_stream(torch.cuda.current_stream(buf.device))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(side)
         plan.launch(side.cuda_stream)
+        e1.record(side)
         bad = plan.finish()
+        if timing is not None:
+            timing["decode_ms"] = e0.elapsed_time(e1)
         plan.close()
         if bad:
             raise RuntimeError(f"{bad} page(s) failed to decode")

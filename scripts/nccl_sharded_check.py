@@ -25,12 +25,14 @@ if rank == owner:
     stream[: len(s)] = torch.from_numpy(s).cuda()
     stream = stream[: len(s)]
 dec = bg.BrotligDecoder(local)
-shard, (lo, hi), nbytes = decode_sharded_stream(stream, owner, cuda_decode_fn(dec), device=torch.device("cuda", local))
+timing = {}
+shard, (lo, hi), nbytes = decode_sharded_stream(stream, owner, cuda_decode_fn(dec, timing), device=torch.device("cuda", local),
+                                                capacity=len(data) + 4096, timing=timing)   # one collective: [size | stream]
 geo = StreamGeometry(38, 65536, 4321, len(data))
 want = data[lo * 65536: lo * 65536 + geo.range_bytes(lo, hi)]
 ok = torch.tensor([int(np.array_equal(shard.cpu().numpy(), want))], device="cuda")
 dist.all_reduce(ok, op=dist.ReduceOp.MIN)
 if rank == 0:
-    print("SHARDED OK" if int(ok.item()) == 1 else "SHARDED MISMATCH", "world", world, "broadcast bytes", nbytes)
+    print("SHARDED OK" if int(ok.item()) == 1 else "SHARDED MISMATCH", "world", world, "stream bytes", nbytes, timing)
 dist.destroy_process_group()
 sys.exit(0 if int(ok.item()) == 1 else 1)

@@ -71,7 +71,7 @@ int emul_decode_stream(const uint8_t* src, uint32_t src_size, uint8_t* dst, uint
       job.out_size = e.out_size;
       job.allow_delta = si.preconditioned;
       bgxk::PageResult results[64];
-      coll += wemu::run_block(2, [&] { results[wemu::thread_id()] = bgxk::decode_page_cta(job, sm); });
+      coll += wemu::run_block(2, [&] { results[wemu::thread_id()] = bgxk::decode_page_cta(job, sm, true); });
       res = results[0];
       for (int l = 1; l < 64; ++l)
         if (results[l].status != res.status || results[l].is_delta != res.is_delta) res.status |= 0x80000000u;

@@ -59,10 +59,14 @@ def _worker(rank, world, port, stream_np, expected_np, q):
 
     owner = 1
     src = torch.from_numpy(stream_np.copy()) if rank == owner else None
-    shard, (lo, hi), nbytes = decode_sharded_stream(src, owner, oracle_decode_fn, device=torch.device("cpu"))
     geo = StreamGeometry.parse(bytes(stream_np[:16]))
-    want = expected_np[lo * geo.page_size: lo * geo.page_size + geo.range_bytes(lo, hi)]
-    ok = bool(np.array_equal(shard.numpy(), want)) and nbytes == len(stream_np)
+    ok = True
+    # once with the size riding inside the one broadcast (every rank knows an upper bound), once with the 8-byte
+    # control pre-broadcast of the size
+    for capacity in (len(stream_np) + 1000, None):
+        shard, (lo, hi), nbytes = decode_sharded_stream(src, owner, oracle_decode_fn, device=torch.device("cpu"), capacity=capacity)
+        want = expected_np[lo * geo.page_size: lo * geo.page_size + geo.range_bytes(lo, hi)]
+        ok = ok and bool(np.array_equal(shard.numpy(), want)) and nbytes == len(stream_np)
     gathered = [None] * world
     dist.all_gather_object(gathered, (rank, lo, hi, ok))
     if rank == 0:
