@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/brotlig_b200.h"
@@ -638,6 +639,113 @@ int bgx_decode_batch_host(bgx_context* ctx, uint32_t n, const uint8_t* const* in
     if (kernel_ms) *kernel_ms += sum;
     for (uint32_t i = 0; i < n; ++i) output_sizes[i] = info[i].uncompressed_size;
   }
+  return rc;
+}
+
+int bgx_decode_host_progress(bgx_context* ctx, uint32_t input_size, const uint8_t* input, uint32_t* output_size, uint8_t* output,
+                             double* kernel_ms, bgx_progress_fn progress, void* user, uint32_t pages_per_group) {
+  if (!progress) return bgx_decode_host(ctx, input_size, input, output_size, output, kernel_ms);
+  BGX_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (input_size < bgx::kStreamHeaderBytes) { ctx->err = "stream shorter than its header"; return bgx::kErrCorruptStream; }
+  StreamInfo si;
+  int rc = bgx::parse_stream_header(input, &si);
+  if (rc) return rc;
+  if (si.uncompressed_size > *output_size) { ctx->err = "output buffer too small"; return bgx::kErrGeneric; }
+  if (si.preconditioned) {
+    // a page range of a texture scatters into the whole texture: one launch, then the per-page reports
+    rc = bgx_decode_host(ctx, input_size, input, output_size, output, kernel_ms);
+    for (uint32_t p = 0; p < si.num_pages && !rc; ++p)
+      if (progress(user, p, si.num_pages)) break;
+    return rc;
+  }
+  const size_t in_cap = ((size_t)input_size + bgx::kInputSlackBytes + 255u) & ~(size_t)255u;
+  if (grow(ctx, &ctx->d_in, &ctx->d_in_cap, in_cap)) return bgx::kErrGeneric;
+  if (grow(ctx, &ctx->d_out, &ctx->d_out_cap, ((size_t)si.uncompressed_size + 255u) & ~(size_t)255u)) return bgx::kErrGeneric;
+  BGX_CUDA(ctx, cudaMemcpyAsync(ctx->d_in, input, input_size, cudaMemcpyHostToDevice, ctx->stream));
+  // groups of pages: the callback can stop the decode between two groups (BrotligDecoder.cpp:318-325 stops a worker
+  // between two pages); the pages that were not decoded stay zero, as after the reference's memset (:448)
+  uint32_t group = pages_per_group ? pages_per_group : std::max<uint32_t>(16u, (si.num_pages + 15u) / 16u);
+  size_t done_bytes = 0;
+  bool aborted = false;
+  for (uint32_t b = 0; b < si.num_pages && !aborted; b += group) {
+    const uint32_t c = std::min<uint32_t>(group, si.num_pages - b);
+    size_t produced = (size_t)c * si.page_size;
+    if (b + c == si.num_pages && si.last_page_size) produced -= si.page_size - si.last_page_size;
+    bgx_stream s;
+    memset(&s, 0, sizeof s);
+    s.d_src = ctx->d_in;
+    s.src_size = input_size;
+    s.src_capacity = (input_size + 15u) & ~15u;
+    s.d_dst = ctx->d_out + (size_t)b * si.page_size;
+    s.dst_capacity = (uint32_t)produced;
+    s.page_begin = b;
+    s.page_count = c;
+    memcpy(s.header, input, std::min<uint32_t>(16, input_size));
+    bgx_plan* plan = nullptr;
+    rc = plan_create_impl(ctx, &s, 1, &plan, true);
+    if (rc) return rc;
+    struct PlanGuard { bgx_plan* p; ~PlanGuard() { bgx_plan_destroy(p); } } plan_guard{plan};
+    BGX_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    rc = launch_range(ctx, plan, 0, 1, 0, ctx->stream);
+    if (rc) return rc;
+    BGX_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    BGX_CUDA(ctx, cudaMemcpyAsync(output + (size_t)b * si.page_size, s.d_dst, produced, cudaMemcpyDeviceToHost, ctx->stream));
+    plan->last_stream = ctx->stream;
+    plan->groups_used = 1;
+    rc = bgx_plan_finish(ctx, plan, nullptr);
+    if (rc) return rc;
+    float ms = 0;
+    BGX_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    if (kernel_ms) *kernel_ms += ms;
+    done_bytes = (size_t)b * si.page_size + produced;
+    for (uint32_t p = b; p < b + c; ++p)
+      if (progress(user, p, si.num_pages)) { aborted = true; break; }
+  }
+  if (aborted && done_bytes < si.uncompressed_size) memset(output + done_bytes, 0, si.uncompressed_size - done_bytes);
+  *output_size = si.uncompressed_size;
+  return bgx::kOk;
+}
+
+// One process, several devices: the streams of the batch are split over the contexts (size balanced, whole streams,
+// no inter-GPU traffic -- pages and streams are independent) and every context decodes its share on its own host thread.
+int bgx_decode_batch_host_multi(bgx_context* const* ctxs, uint32_t n_ctx, uint32_t n, const uint8_t* const* inputs,
+                                const uint32_t* input_sizes, uint8_t* const* outputs, uint32_t* output_sizes, double* kernel_ms) {
+  if (n_ctx == 0) return bgx::kErrGeneric;
+  if (n_ctx == 1) return bgx_decode_batch_host(ctxs[0], n, inputs, input_sizes, outputs, output_sizes, kernel_ms);
+  // longest-processing-time-first by compressed size
+  std::vector<uint32_t> order(n);
+  for (uint32_t i = 0; i < n; ++i) order[i] = i;
+  std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return input_sizes[a] != input_sizes[b] ? input_sizes[a] > input_sizes[b] : a < b; });
+  std::vector<std::vector<uint32_t>> share(n_ctx);
+  std::vector<uint64_t> load(n_ctx, 0);
+  for (uint32_t i : order) {
+    const uint32_t r = (uint32_t)(std::min_element(load.begin(), load.end()) - load.begin());
+    share[r].push_back(i);
+    load[r] += input_sizes[i];
+  }
+  std::vector<int> rcs(n_ctx, 0);
+  std::vector<double> ms(n_ctx, 0.0);
+  std::vector<std::thread> th;
+  for (uint32_t r = 0; r < n_ctx; ++r) {
+    th.emplace_back([&, r] {
+      const std::vector<uint32_t>& mine = share[r];
+      if (mine.empty()) return;
+      std::vector<const uint8_t*> in(mine.size());
+      std::vector<uint32_t> isz(mine.size()), osz(mine.size());
+      std::vector<uint8_t*> out(mine.size());
+      for (size_t k = 0; k < mine.size(); ++k) { in[k] = inputs[mine[k]]; isz[k] = input_sizes[mine[k]]; out[k] = outputs[mine[k]]; osz[k] = output_sizes[mine[k]]; }
+      rcs[r] = bgx_decode_batch_host(ctxs[r], (uint32_t)mine.size(), in.data(), isz.data(), out.data(), osz.data(), &ms[r]);
+      for (size_t k = 0; k < mine.size(); ++k) output_sizes[mine[k]] = osz[k];
+    });
+  }
+  for (auto& t : th) t.join();
+  int rc = 0;
+  double worst = 0;
+  for (uint32_t r = 0; r < n_ctx; ++r) {
+    if (rcs[r] && !rc) rc = rcs[r];
+    worst = std::max(worst, ms[r]);
+  }
+  if (kernel_ms) *kernel_ms += worst;   // devices run concurrently: the slowest one is the batch's kernel time
   return rc;
 }
 

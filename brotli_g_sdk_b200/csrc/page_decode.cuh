@@ -99,6 +99,7 @@ enum : uint32_t {
   kPageErrDistance = 2,     // distance 0 or reaching before the start of the page
   kPageErrLiterals = 4,     // a round needs more literals than it carries
   kPageErrTable = 8,        // malformed prefix-code description
+  kPageErrHang = 16,        // the two warps of the page stopped handing rounds over (cannot happen on a valid stream)
 };
 
 struct HuffAux {
@@ -398,16 +399,16 @@ BGX_DEV void lut_fill_coop(uint16_t* lut, uint32_t rev, uint32_t len, uint16_t e
 // Builds LUT + canonical arrays from the code lengths in `lens[0..n)` (shared memory).
 // Canonical order = (length, symbol index), as GenerateHuffmanTable (BrotligHuffmanTable.cpp:44-71).
 template <int BITS, typename SortedT>
-BGX_DEV void build_table(WarpSmem* sm, const uint8_t* lens, uint32_t n, uint16_t* lut, HuffAux& aux, SortedT* sorted,
-                         uint32_t lane) {
+BGX_DEV uint32_t build_table(WarpSmem* sm, const uint8_t* lens, uint32_t n, uint16_t* lut, HuffAux& aux, SortedT* sorted,
+                             uint32_t lane) {
   uint32_t* cnt = sm->scratch;        // [16]
-  uint32_t* next = sm->scratch + 16;  // [16] running position in `sorted` per length
+  uint32_t* next = sm->scratch + 16;  // [16] running position in `sorted` per length; [0]: the code is usable
   if (lane < 16) cnt[lane] = 0;
   __syncwarp();
   for (uint32_t s = lane; s < n; s += 32) atomicAdd(&cnt[lens[s]], 1u);
   __syncwarp();
   if (lane == 0) {
-    uint32_t code = 0, off = 0;
+    uint32_t code = 0, off = 0, kraft = 0;
     cnt[0] = 0;
     aux.limit[0] = 0;
     aux.base[0] = 0;
@@ -418,7 +419,12 @@ BGX_DEV void build_table(WarpSmem* sm, const uint8_t* lens, uint32_t n, uint16_t
       aux.limit[L] = (uint16_t)(lim > 0x8000u ? 0x8000u : lim);
       next[L] = off;
       off += cnt[L];
+      kraft += cnt[L] << (15 - L);
     }
+    // A prefix code must be complete (Kraft sum exactly 1; RFC 7932 section 3.2), or consist of a single symbol. The
+    // reference trusts the lengths (BrotligHuffmanTable.cpp:44-71,135-145): an over-subscribed set overwrites table
+    // entries, an incomplete one leaves entries of the previous page in place. Both are rejected here.
+    next[0] = (kraft == 0x8000u || off == 1u) ? 0u : 1u;
   }
   __syncwarp();
   for (uint32_t s0 = 0; s0 < n; s0 += 32) {
@@ -456,6 +462,7 @@ BGX_DEV void build_table(WarpSmem* sm, const uint8_t* lens, uint32_t n, uint16_t
     }
     __syncwarp();
   }
+  return next[0] ? kPageErrTable : 0u;
 }
 
 // Reads one prefix-code description (trivial / simple / complex) and builds its tables.
@@ -513,6 +520,12 @@ BGX_DEV uint32_t load_table(WarpSmem* sm, BitRd& rd, PageIn& in, uint32_t alphab
   }
   const uint32_t bad = __ballot_sync(kFull, myread > 9u);
   if (bad) return kPageErrTable;   // reference: out-of-bounds table index
+  {
+    // the code-length code itself must be a complete prefix code or a single symbol (see build_table)
+    const uint32_t used = __ballot_sync(kFull, myread != 0u);
+    const uint32_t kraft = __reduce_add_sync(kFull, myread ? (512u >> myread) : 0u);
+    if (kraft != 512u && __popc(used) != 1) return kPageErrTable;
+  }
   __syncwarp();
   // canonical codes over symbols 0..ncl-1 (GenerateHuffmanTable is called with size = ncl, :145),
   // but the per-length counts come from every length that was read (:135-142)
@@ -562,8 +575,7 @@ BGX_DEV uint32_t load_table(WarpSmem* sm, BitRd& rd, PageIn& in, uint32_t alphab
     filled += __reduce_add_sync(kFull, active ? run : 0u);
   }
   __syncwarp();
-  build_table<BITS, SortedT>(sm, lens, alphabet, lut, aux, sorted, lane);
-  return 0;
+  return build_table<BITS, SortedT>(sm, lens, alphabet, lut, aux, sorted, lane);
 }
 
 
@@ -657,18 +669,22 @@ BGX_DEV void mbar_arrive(saddr_t a) {
   asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(a) : "memory");
 #endif
 }
-BGX_DEV void mbar_wait(saddr_t a, uint32_t parity) {
-#ifdef BGX_EMULATED
-  wemu::mbar_wait(reinterpret_cast<uint64_t*>(a), parity);
-#else
-  // try_wait suspends the warp until the phase completes or a time limit passes. Without the optional time-limit
-  // operand that limit is short: the waiting side of a round then issued ~200 instructions of this loop per round
-  // (17 % of all issued instructions of the kernel). With a long limit the warp sleeps until the arrive wakes it.
-  uint32_t done;
+// Waits for the phase with this parity to complete. Returns false when it did not within kWaitLimitCycles (about a
+// second): a hand-over that a valid stream cannot produce. Both warps of the page then leave with kPageErrHang, so a
+// corrupt stream can never hang the persistent kernel (the emulator's dead-lock detection plays this role on the CPU).
 #ifndef BGX_WAIT_HINT_NS
 #define BGX_WAIT_HINT_NS 0x989680
 #endif
-  do {
+constexpr long long kWaitLimitCycles = 2000000000ll;
+BGX_DEV bool mbar_wait(saddr_t a, uint32_t parity) {
+#ifdef BGX_EMULATED
+  wemu::mbar_wait(reinterpret_cast<uint64_t*>(a), parity);
+  return true;
+#else
+  // try_wait suspends the warp until the phase completes or a (hardware-bounded) time limit passes
+  uint32_t done;
+  long long t0 = 0;
+  for (;;) {
 #if BGX_WAIT_HINT_NS > 0
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -680,7 +696,11 @@ BGX_DEV void mbar_wait(saddr_t a, uint32_t parity) {
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(a), "r"(parity) : "memory");
 #endif
-  } while (!done);
+    if (done) return true;
+    const long long now = clock64();
+    if (t0 == 0) t0 = now;
+    else if (now - t0 > kWaitLimitCycles) return false;
+  }
 #endif
 }
 // the whole warp signals: its earlier shared-memory accesses are ordered before the elected lane's arrive
@@ -702,20 +722,22 @@ struct ProdCtx {
   uint32_t lit_tail;       // literals decoded so far
   uint32_t lit_head_p;     // literals that the rounds published so far consume
 
-  // waits until slot rnd % kQ is free
-  BGX_DEV void acquire_slot() {
+  // waits until slot rnd % kQ is free; false = the consumer stopped taking rounds (kPageErrHang is set)
+  BGX_DEV bool acquire_slot() {
     while (synced + kQ <= rnd) {   // the slot still holds round rnd - kQ: wait until the consumer is done with it
-      mbar_wait(empty_a + 8u * (synced & (kQ - 1u)), (synced / kQ) & 1u);
+      if (!mbar_wait(empty_a + 8u * (synced & (kQ - 1u)), (synced / kQ) & 1u)) { hang(); return false; }
       ++synced;
     }
+    return true;
   }
+  BGX_DEV void hang() { if (lane == 0) sm->ctl.err = kPageErrHang; }
   // the literal ring must hold `newlits` more literals next to those of every round the consumer may still be
   // working on (rounds >= synced): takes more empty[] phases while that helps; false if they cannot fit at all
   BGX_DEV bool wait_lit_room(uint32_t newlits) {
     uint32_t head_known = synced == rnd ? lit_head_p : sm->ctl.phead[synced & (kQ - 1u)];
     bool fits = (lit_tail - head_known) + newlits <= kLitQ;
     while (!fits && synced < rnd) {
-      mbar_wait(empty_a + 8u * (synced & (kQ - 1u)), (synced / kQ) & 1u);
+      if (!mbar_wait(empty_a + 8u * (synced & (kQ - 1u)), (synced / kQ) & 1u)) { hang(); return false; }
       ++synced;
       head_known = synced == rnd ? lit_head_p : sm->ctl.phead[synced & (kQ - 1u)];
       fits = (lit_tail - head_known) + newlits <= kLitQ;
@@ -766,7 +788,7 @@ BGX_COLD bool slow_round(SlowRound* a) {
   bool first = true;
   for (;;) {
     const uint32_t work = __ballot_sync(kFull, (rem_ins | rem_cpy) != 0u);
-    if (!first) pc.acquire_slot();
+    if (!first && !pc.acquire_slot()) return false;
     first = false;
     const uint32_t a0 = work ? (uint32_t)(__ffs((int)work) - 1) : 32u;   // first command with something left
     uint32_t v_ins = rem_ins, v_cpy = rem_cpy;
@@ -883,7 +905,7 @@ BGX_DEV void producer_warp(const PageJob& job, WarpSmem* sm) {
   }
   const uint32_t postfix_mask = (1u << npostfix) - 1u;
   for (;;) {
-    pc.acquire_slot();
+    if (!pc.acquire_slot()) break;
     br_topup1(rd, in);
     // ---- one command per lane, speculatively: the lanes behind the sentinel consume nothing. Straight-line code
     //      with two window refills (after the insert&copy part and after the distance part); only 24-bit extra
@@ -1121,7 +1143,10 @@ BGX_DEV void consumer_warp(const PageJob& job, WarpSmem* sm) {
 
   for (uint32_t r = 0;; ++r) {
     const uint32_t q = r & (kQ - 1u);
-    mbar_wait(full_a + 8u * q, (r / kQ) & 1u);
+    if (!mbar_wait(full_a + 8u * q, (r / kQ) & 1u)) {   // the producer stopped publishing
+      if (lane == 0) sm->ctl.err = kPageErrHang;
+      break;
+    }
     const uint2 cw = lds_u32x2(rb_a + (uint32_t)sizeof(RoundBuf) * q + 8u * lane);
     if (cw.y & kPkAbort) break;
     const uint32_t dist = cw.x;                        // resolved and validated by the producer

@@ -46,6 +46,23 @@ int bgx_decode_host(bgx_context* ctx, uint32_t input_size, const uint8_t* input,
 int bgx_decode_batch_host(bgx_context* ctx, uint32_t n, const uint8_t* const* inputs, const uint32_t* input_sizes,
                           uint8_t* const* outputs, uint32_t* output_sizes, double* kernel_ms);
 
+/* bgx_decode_host with the per-page feedback of BrotliG::DecodeCPU (/root/reference/src/BrotligDecoder.cpp:318-325:
+ * the callback runs after a page, a non-zero return stops the decode). The stream is decoded in groups of
+ * `pages_per_group` pages (0 = a sixteenth of the stream, at least 16); after each group progress(user, page, num_pages)
+ * is called for its pages in order. When it returns non-zero no further group is decoded, the bytes of the pages that
+ * were not decoded are zero (the reference memsets the output first, :448) and the call returns 0 like the reference. */
+typedef int (*bgx_progress_fn)(void* user, uint32_t page_index, uint32_t num_pages);
+int bgx_decode_host_progress(bgx_context* ctx, uint32_t input_size, const uint8_t* input, uint32_t* output_size, uint8_t* output,
+                             double* kernel_ms, bgx_progress_fn progress, void* user, uint32_t pages_per_group);
+
+/* bgx_decode_batch_host over several devices of one box from ONE process: ctxs[] are contexts created on different
+ * devices; whole streams are assigned to them (balanced by compressed size, no inter-GPU traffic: pages and streams are
+ * independent, /root/reference/src/decoder/PageDecoder.cpp:126-153) and decoded concurrently, one host thread per device.
+ * *kernel_ms is incremented by the slowest device's kernel time. (The one-process-per-GPU launcher with the NCCL
+ * broadcast of a sharded stream is brotli_g_sdk_b200/multi_gpu.py.) */
+int bgx_decode_batch_host_multi(bgx_context* const* ctxs, uint32_t n_ctx, uint32_t n, const uint8_t* const* inputs,
+                                const uint32_t* input_sizes, uint8_t* const* outputs, uint32_t* output_sizes, double* kernel_ms);
+
 /* ---- device-resident interface (no host<->device traffic in the decode path) ---- */
 typedef struct bgx_stream {
   const uint8_t* d_src;      /* device pointer to the stream (16-byte aligned) */

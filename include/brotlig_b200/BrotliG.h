@@ -41,8 +41,11 @@ extern "C" {
 // Size of the decompressed data, from the stream header only.
 uint32_t BROTLIG_API DecompressedSize(uint8_t* src);
 // Same contract as the reference's DecodeCPU: *output_size is the buffer size on entry and the
-// decompressed size on return; feedbackProc (nullable) is called once with progress "100" after the
-// stream has been decoded (the GPU decodes all pages of a stream in one launch).
+// decompressed size on return; feedbackProc (nullable) is called for every page with the progress in
+// percent (the stream is then decoded in groups of pages and the pages of a finished group are reported
+// in order); when it returns true no further group is decoded, the rest of the output stays zero and
+// the call returns BROTLIG_OK -- the reference's behaviour (BrotligDecoder.cpp:318-325,448,490).
+// Re-entrant: concurrent callers use separate decoder contexts.
 BROTLIG_ERROR BROTLIG_API DecodeCPU(uint32_t input_size, const uint8_t* src, uint32_t* output_size, uint8_t* output,
                                     BROTLIG_Feedback_Proc feedbackProc);
 }

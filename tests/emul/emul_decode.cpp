@@ -99,6 +99,22 @@ void emul_stats(uint64_t* out14, int reset) {
   if (reset) memset(&bgxk::emu_stats(), 0, sizeof(bgxk::EmuStats));
 }
 #endif
+// build_table on a given set of code lengths (n <= 728): returns the status every lane agreed on (0 = usable)
+uint32_t emul_table_status(const uint8_t* lens, uint32_t n) {
+  bgxk::WarpSmem* sm = new bgxk::WarpSmem();
+  memset(sm, 0, sizeof(*sm));
+  memcpy(sm->ring, lens, n);
+  uint32_t st[32];
+  wemu::run_warp([&] {
+    st[wemu::lane()] = bgxk::build_table<bgxk::kCmdLutBits, uint16_t>(sm, sm->ring, n, sm->lut_cmd, sm->aux[0], sm->sorted_cmd, (uint32_t)wemu::lane());
+  });
+  uint32_t r = st[0];
+  for (int l = 1; l < 32; ++l)
+    if (st[l] != r) r = 0xffffffffu;
+  delete sm;
+  return r;
+}
+
 uint32_t emul_warp_smem_bytes() { return (uint32_t)sizeof(bgxk::WarpSmem); }
 
 // The host-pointer pipeline's segment planner (host_plan.h), for the CPU unit test. Writes 7 numbers per segment

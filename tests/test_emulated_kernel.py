@@ -59,3 +59,45 @@ def test_emulated_kernel_rejects_garbage_without_writing_out_of_bounds(sdk, emul
             emulator.decode(bad, expect_rc=0)
         except AssertionError as e:
             assert "rc 14" in str(e) or "status" in str(e), str(e)
+
+
+def test_prefix_code_descriptions_must_be_complete(emulator):
+    """Kraft sum of the code lengths: complete codes and single-symbol codes are accepted, over- and under-subscribed
+    ones end in kPageErrTable (the reference trusts them: BrotligHuffmanTable.cpp:44-71,135-145)"""
+    import ctypes
+
+    def status(lens):
+        a = np.zeros(728, np.uint8)
+        a[: len(lens)] = lens
+        emulator.lib.emul_table_status.restype = ctypes.c_uint32
+        return int(emulator.lib.emul_table_status(ctypes.c_void_p(a.ctypes.data), ctypes.c_uint32(728)))
+
+    assert status([1, 1]) == 0
+    assert status([1, 2, 3, 3]) == 0
+    assert status([2, 2, 2, 2]) == 0
+    assert status([15] * 2 + [14] + [13] + [12] + [11] + [10] + [9] + [8] + [7] + [6] + [5] + [4] + [3] + [2] + [1]) == 0
+    assert status([3]) == 0                      # a single symbol
+    assert status([1, 1, 1]) == 8                # over-subscribed
+    assert status([1, 2, 2, 2]) == 8
+    assert status([2, 2, 2]) == 8                # incomplete
+    assert status([1, 3]) == 8
+
+
+def test_texture_header_with_a_lying_pitch_is_rejected(sdk, emulator):
+    """PreconditionHeader fields are untrusted: a pitch smaller than a row of blocks (or sizes that do not add up) must
+    not reach the de-conditioning scatter. 16-byte header: BC1, 64 x 64 blocks, pitch 8, 512 bytes, one raw page."""
+    import ctypes
+    w0 = 5 | (0xFA << 8) | (1 << 16)                                   # id, magic, 1 page
+    w1 = 1 | (512 << 2) | (1 << 20)                                    # 64 KiB pages, last page 512 bytes, preconditioned
+    p0 = (63 << 2) | (63 << 17)                                        # 64 x 64 blocks
+    p1 = 1 | (0 << 8) | ((8 - 1) << 13)                                # BC1, 1 mip, pitch 8 bytes (a row needs 512)
+    hdr = np.array([w0, w1, p0, p1], dtype="<u4").view(np.uint8)
+    stream = np.concatenate([hdr, np.array([512], dtype="<u4").view(np.uint8), np.zeros(512, np.uint8)])
+    out = np.zeros(512 + 64, np.uint8)
+    st = (ctypes.c_uint32 * 1)()
+    fl = (ctypes.c_uint32 * 1)()
+    coll = ctypes.c_uint64(0)
+    rc = emulator.lib.emul_decode_stream(ctypes.c_void_p(stream.ctypes.data), ctypes.c_uint32(len(stream)), ctypes.c_void_p(out.ctypes.data),
+                                         ctypes.c_uint32(512), st, fl, ctypes.byref(coll))
+    assert rc == 14, rc            # BROTLIG_ERROR_CORRUPT_STREAM
+    assert not out.any()
