@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(kPageThreads, BGX_CTAS_PER_SM) bgx_decode_page
     if (!in_bounds) {
       status = bgxk::kPageErrTable;
     } else if (e.in_size == e.out_size) {
-      bgxk::copy_page_cta(out, in, e.out_size);
+      bgxk::copy_page_cta(out, in, e.out_size, &sm);
     } else if (e.in_size < 8u || (e.in_off & 3u) != 0u) {
       status = bgxk::kPageErrTable;
     } else {

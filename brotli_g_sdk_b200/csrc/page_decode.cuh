@@ -430,6 +430,7 @@ BGX_DEV uint32_t build_table(WarpSmem* sm, const uint8_t* lens, uint32_t n, uint
   for (uint32_t s0 = 0; s0 < n; s0 += 32) {
     const uint32_t s = s0 + lane;
     const uint32_t L = s < n ? lens[s] : 0u;
+    if (__ballot_sync(kFull, L != 0u) == 0u) continue;   // (most of the 728 / 544 symbols of a page are unused)
     const uint32_t m = __match_any_sync(kFull, L);
     const uint32_t rank = __popc(m & ((1u << lane) - 1u));
     uint32_t idx = 0, code = 0;
@@ -1545,11 +1546,73 @@ BGX_DEV void copy_page_warp(uint8_t* dst, const uint8_t* src, uint32_t n) {
 }
 
 // both warps of the page's CTA take half of a raw page each
-BGX_DEV void copy_page_cta(uint8_t* dst, const uint8_t* src, uint32_t n) {
+BGX_DEV void copy_page_cta_ldst(uint8_t* dst, const uint8_t* src, uint32_t n) {
   uint32_t h = ((n >> 1) + 255u) & ~255u;
   if (h > n) h = n;
   if (warp_index() == 0) copy_page_warp(dst, src, h);
   else copy_page_warp(dst + h, src + h, n - h);
+}
+
+#if !defined(BGX_EMULATED) && BGX_RAW_PATH == 2
+// Raw page through the copy engines: the page is contiguous in the stream and in the output, so it moves in 4 KiB
+// chunks global -> shared (cp.async: 16-byte units when the page sits on a 16-byte boundary of the stream, 8-byte units
+// when it sits 8 bytes off one -- the usual layout: 8-byte header + 4n-byte page table) and shared -> global as ONE TMA
+// bulk store per chunk (cp.async.bulk.global.shared::cta, SASS UBLKCP) issued by one elected thread: no thread touches
+// the data, the output leaves as 4 KiB bursts. Three chunks rotate through the page arena (the tables are not in use).
+template <int G>
+BGX_DEV void copy_page_cta_bulk(uint8_t* dst, const uint8_t* src, uint32_t n, WarpSmem* sm) {
+  constexpr uint32_t kChunk = 4096, kStages = 3;
+  static_assert(offsetof(WarpSmem, mbar) >= kStages * kChunk + 128, "the staging chunks fit the page arena below its mbarriers");
+  const uint32_t tid = threadIdx.x;
+  const saddr_t buf = (saddr(sm) + 127u) & ~127u;
+  const uint32_t nchunks = n / kChunk;
+  auto issue = [&](uint32_t c) {
+    const uint8_t* g = src + (size_t)c * kChunk;
+    const saddr_t st = buf + (c % kStages) * kChunk;
+#pragma unroll
+    for (uint32_t i = 0; i < kChunk / (64u * G); ++i) {
+      const uint32_t o = (i * 64u + tid) * G;
+      if (G == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(st + o), "l"(g + o) : "memory");
+      else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(st + o), "l"(g + o) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  for (uint32_t c = 0; c < kStages - 1 && c < nchunks; ++c) issue(c);
+  for (uint32_t c = 0; c < nchunks; ++c) {
+    if (c + kStages - 1 < nchunks) {
+      // the stage of chunk c + 2 is the stage of chunk c - 1: its bulk store must have finished reading shared memory
+      if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      __syncthreads();
+      issue(c + kStages - 1);
+      asm volatile("cp.async.wait_group %0;" ::"n"(kStages - 1) : "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the cp.async writes become visible to the bulk copy
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + (size_t)c * kChunk),
+                   "r"(buf + (c % kStages) * kChunk), "r"(kChunk) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+  }
+  if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  __syncthreads();
+  const uint32_t done = nchunks * kChunk;
+  if (done < n) copy_page_cta_ldst(dst + done, src + done, n - done);
+}
+#endif
+
+BGX_DEV void copy_page_cta(uint8_t* dst, const uint8_t* src, uint32_t n, WarpSmem* sm) {
+#if !defined(BGX_EMULATED) && BGX_RAW_PATH == 2
+  const uintptr_t a = reinterpret_cast<uintptr_t>(dst), b = reinterpret_cast<uintptr_t>(src);
+  if ((a & 15u) == 0 && n >= 8192u) {
+    if ((b & 15u) == 0) { copy_page_cta_bulk<16>(dst, src, n, sm); return; }
+    if ((b & 7u) == 0) { copy_page_cta_bulk<8>(dst, src, n, sm); return; }
+  }
+#endif
+  (void)sm;
+  copy_page_cta_ldst(dst, src, n);
 }
 
 }  // namespace bgxk

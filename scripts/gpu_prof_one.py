@@ -8,10 +8,16 @@ import brotli_g_sdk_b200 as b
 from brotli_g_sdk_b200 import datagen
 kind, mib, copies = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
 launches = int(sys.argv[4]) if len(sys.argv) > 4 else 1
-gen = {"text": datagen.text_like, "lowent": datagen.low_entropy, "random": datagen.random_bytes,
+gen = {"text": datagen.text_like, "lowent": datagen.low_entropy, "random": datagen.random_bytes, "texture": None,
        "binary": datagen.structured_binary, "mixed": datagen.mixed}[kind]
-data = gen(mib << 20, seed=21)
-s = b.Encode(data)
+if kind == "texture":     # a 16 MiB BC3 texture with swizzle + delta pre-conditioning, whatever the size argument says
+    from brotli_g_sdk_b200.encoder import DataconditionParams
+    data = datagen.bc_texture(1024, 1024, 3, seed=21)
+    s = b.Encode(data, dcParams=DataconditionParams(precondition=True, swizzle=True, delta_encode=True, format=3,
+                                                    width_blocks=1024, height_blocks=1024))
+else:
+    data = gen(mib << 20, seed=21)
+    s = b.Encode(data)
 dec = b.BrotligDecoder(0)
 sd, keep = [], []
 for c in range(copies):

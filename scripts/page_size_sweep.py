@@ -1,6 +1,9 @@
 """BASELINE configs[4]: page-size sweep on the mixed-entropy payload, one GPU.
 32/64/128 KiB via the stream header's PageSizeIdx; 4/8/16 KiB "pages" as single-page streams
-(NumPages = 1, LastPageSize = n) batched by the thousands. Writes gpurun_out/page_size_sweep.json."""
+(NumPages = 1, LastPageSize = n) batched by the thousands. Writes gpurun_out/page_size_sweep.json.
+usage: page_size_sweep.py [total MiB per size=256] [kind=mixed] [sizes=4096,...,131072]
+SWEEP_SINGLE=1: exactly one launch per size and no timing loop (for `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum
+-k regex:bgx_decode_pages`: launch i of the capture is size i of the list)."""
 import json, os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -39,11 +42,12 @@ for ps in sizes:
     plan = dec.plan(descs)
     ts = torch.cuda.Stream()
     torch.cuda.synchronize()
-    for _ in range(3):
+    single = os.environ.get("SWEEP_SINGLE") == "1"
+    for _ in range(0 if single else 3):
         plan.launch(ts.cuda_stream)
     assert plan.finish() == 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    K = 5
+    K = 1 if single else 5
     e0.record(ts)
     for _ in range(K):
         plan.launch(ts.cuda_stream)
@@ -59,4 +63,4 @@ for ps in sizes:
     print(ps, res[str(ps)], flush=True)
     del keep, plan
 os.makedirs("gpurun_out", exist_ok=True)
-json.dump(res, open("gpurun_out/page_size_sweep.json", "w"), indent=1)
+json.dump(res, open("gpurun_out/page_size_sweep%s.json" % ("_single" if os.environ.get("SWEEP_SINGLE") == "1" else ""), "w"), indent=1)

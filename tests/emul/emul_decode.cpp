@@ -59,7 +59,7 @@ int emul_decode_stream(const uint8_t* src, uint32_t src_size, uint8_t* dst, uint
     if (!in_bounds) {
       res.status = bgxk::kPageErrTable;
     } else if (e.in_size == e.out_size) {
-      coll += wemu::run_block(2, [&] { bgxk::copy_page_cta(dst + e.out_off, pages + e.in_off, e.out_size); });
+      coll += wemu::run_block(2, [&] { bgxk::copy_page_cta(dst + e.out_off, pages + e.in_off, e.out_size, sm); });
     } else if (e.in_size < 8u || (e.in_off & 3u) != 0u) {
       res.status = bgxk::kPageErrTable;
     } else {
