@@ -18,7 +18,8 @@ its share, no data-path collective). At N = 1 it is the largest single-GPU confi
   cpu_baseline  the reference's own DecodeCPU (oracle/_ref, unmodified, built from /root/reference) on the box's host
              cores over a bounded sample of the same streams
   secondary  (N = 1) BASELINE.json configs[1]: 4 GiB of random bytes -- every page is stored raw, so this is a memcpy
-             upper bound of the page kernel, not a decoder number
+             upper bound of the page kernel, not a decoder number; secondary_texture: configs[2], 4 GiB of pre-conditioned
+             BC3 textures (page kernel + de-conditioning kernel)
   sharded    (N > 1) SURVEY section 8e level 2: single 64 MiB streams living on one rank, replicated with ONE NCCL
              broadcast and decoded by page range on every rank; reported with and without the broadcast time
 --impl reference times the reference CPU decoder alone on the same config (rank 0 only).
@@ -496,6 +497,24 @@ def run_ours(args):
         del keep2, plan2, s2, d2
         torch.cuda.empty_cache()
 
+    # ---------------- second secondary (N = 1): configs[2], 4 GiB of pre-conditioned BC3 textures (page kernel + de-conditioning)
+    secondary_texture = None
+    if world == 1 and not args.no_secondary and args.workload != "texture":
+        s3, d3 = get_unique("texture", 4 << 30, 8, datagen.SEED_CONFIG3)
+        sh3 = share_of("texture", 4 << 30, s3)
+        keep3, plan3 = resident(s3, d3, sh3)
+        st3 = max(3, args.steps // 2)
+        ms3, _ = timed(plan3, st3, 3)
+        ms3 /= st3
+        verify(keep3, sh3, d3, "texture")
+        o3, i3 = float(sum(len(d3[w]) for w in sh3)), float(sum(len(s3[w]) for w in sh3))
+        secondary_texture = {"workload": WORKLOADS["texture"].format(gib=4, n=len(sh3)), "value": o3 / (ms3 / 1e3) / 1e9, "unit": "GB/s",
+                             "ms_per_step": ms3, "kernels_per_step": plan3.info["kernels_per_launch"], "compression_ratio": o3 / i3,
+                             "roofline": {"bound": "hbm", "achieved": (i3 + o3) / (ms3 / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                                          "frac": (i3 + o3) / (ms3 / 1e3) / 1e9 / peak, "traffic": ncu_traffic("texture", i3 + o3)}}
+        del keep3, plan3, s3, d3
+        torch.cuda.empty_cache()
+
     # ---------------- sharded streams (N > 1): one NCCL broadcast per stream, page ranges per rank
     sharded = None
     if world > 1 and not args.no_sharded and args.workload != "texture":
@@ -541,7 +560,7 @@ def run_ours(args):
                          "algorithmic_bytes_per_launch": (all_in + all_out) / world, "per": "GPU", "grid_blocks": grid,
                          "compression_ratio": all_out / all_in},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
-            "secondary": secondary, "sharded": sharded, "bit_exact": True,
+            "secondary": secondary, "secondary_texture": secondary_texture, "sharded": sharded, "bit_exact": True,
         }
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)

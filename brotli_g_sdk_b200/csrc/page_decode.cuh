@@ -53,7 +53,7 @@
 #define BGX_WAIT_SLEEP_NS 0
 #endif
 #ifndef BGX_RAW_PATH
-#define BGX_RAW_PATH 1
+#define BGX_RAW_PATH 2   // 2: raw pages leave through TMA bulk stores (copy_page_cta_bulk); 1: register copies only
 #endif
 
 namespace bgxk {
@@ -108,7 +108,7 @@ struct HuffAux {
 };
 
 #ifndef BGX_Q
-#define BGX_Q 4
+#define BGX_Q 2
 #endif
 constexpr uint32_t kQ = BGX_Q;   // rounds in flight between the producer and the consumer warp (power of two)
 struct RoundBuf {            // one round of <= 32 commands, producer -> consumer (a round never produces more than
@@ -131,8 +131,8 @@ struct WarpSmem {
   uint8_t sorted_lit[bgx::kNumLitSymbols];
   HuffAux aux[3];
   uint32_t lenlut[48];              // [0..23] insert code, [24..47] copy code: base | extra_bits << 16
-  alignas(16) uint32_t scratch[96];  // table build: cnt[16], next[16], 18 code-length-code lengths;
-                                    // decode: [0..31] insert table, [32..159] copy table (uint4)
+  alignas(16) uint32_t scratch[192]; // table build: cnt[16], next[16], 18 code-length-code lengths;
+                                    // consumer: [0..31] insert table, [32..159] wave-1 copies (uint4), [160..191] the other copies
   uint8_t litq[kLitQ];              // literal ring, indexed by page-global literal index
   alignas(16) uint8_t ring[kRing];  // output ring; while tables are read: code lengths [0..727] and the
                                     // 512 x u16 code-length-code LUT [1024..2047]
@@ -155,6 +155,8 @@ BGX_DEV void sts_u8(saddr_t a, uint32_t v) { *reinterpret_cast<uint8_t*>(a) = (u
 BGX_DEV uint32_t lds_u32(saddr_t a) { return *reinterpret_cast<const uint32_t*>(a); }
 BGX_DEV uint2 lds_u32x2(saddr_t a) { return *reinterpret_cast<const uint2*>(a); }
 BGX_DEV void sts_u32(saddr_t a, uint32_t v) { *reinterpret_cast<uint32_t*>(a) = v; }
+BGX_DEV uint4 lds_u32x4(saddr_t a) { return *reinterpret_cast<const uint4*>(a); }
+BGX_DEV void sts_u32x4(saddr_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) { uint32_t* p = reinterpret_cast<uint32_t*>(a); p[0] = x; p[1] = y; p[2] = z; p[3] = w; }
 BGX_DEV void sts_u32x2(saddr_t a, uint32_t x, uint32_t y) { uint32_t* p = reinterpret_cast<uint32_t*>(a); p[0] = x; p[1] = y; }
 BGX_DEV uint32_t ldg_u8(const uint8_t* p) { return *p; }
 BGX_DEV uint32_t ldg_u32(const uint32_t* p) { return *p; }
@@ -169,6 +171,8 @@ BGX_DEV void sts_u8(saddr_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1
 BGX_DEV uint32_t lds_u32(saddr_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 BGX_DEV uint2 lds_u32x2(saddr_t a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
 BGX_DEV void sts_u32(saddr_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+BGX_DEV uint4 lds_u32x4(saddr_t a) { uint4 v; asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v; }
+BGX_DEV void sts_u32x4(saddr_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) { asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory"); }
 BGX_DEV void sts_u32x2(saddr_t a, uint32_t x, uint32_t y) { asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory"); }
 BGX_DEV uint32_t ldg_u8(const uint8_t* p) { uint32_t v; asm volatile("ld.global.u8 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
 BGX_DEV uint32_t ldg_u32(const uint32_t* p) { uint32_t v; asm volatile("ld.global.u32 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
@@ -315,6 +319,7 @@ BGX_DEV void br_skip(BitRd& r, const PageIn& in, uint32_t n) {   // n <= 32
     r.bitpos -= 32u;
   }
 }
+BGX_DEV uint32_t umin32(uint32_t a, uint32_t b) { return a < b ? a : b; }
 BGX_DEV uint32_t shr32(uint32_t v, uint32_t n) { return n >= 32u ? 0u : (v >> n); }
 BGX_DEV uint32_t low_mask(uint32_t n) { return n >= 32u ? 0xffffffffu : ((1u << n) - 1u); }
 BGX_DEV uint32_t br_read(BitRd& r, const PageIn& in, uint32_t n) {   // n <= 32
@@ -463,7 +468,9 @@ BGX_DEV uint32_t build_table(WarpSmem* sm, const uint8_t* lens, uint32_t n, uint
     }
     __syncwarp();
   }
-  return next[0] ? kPageErrTable : 0u;
+  const uint32_t unusable = next[0];
+  __syncwarp();   // (the next table's description reuses this scratch: every lane has read the flag before that)
+  return unusable ? kPageErrTable : 0u;
 }
 
 // Reads one prefix-code description (trivial / simple / complex) and builds its tables.
@@ -725,6 +732,9 @@ struct ProdCtx {
 
   // waits until slot rnd % kQ is free; false = the consumer stopped taking rounds (kPageErrHang is set)
   BGX_DEV bool acquire_slot() {
+#ifdef BGX_HANDOVER_SYNCTHREADS
+    return true;   // (lock-step verification build: the CTA barrier in publish() is the hand-over)
+#endif
     while (synced + kQ <= rnd) {   // the slot still holds round rnd - kQ: wait until the consumer is done with it
       if (!mbar_wait(empty_a + 8u * (synced & (kQ - 1u)), (synced / kQ) & 1u)) { hang(); return false; }
       ++synced;
@@ -735,6 +745,10 @@ struct ProdCtx {
   // the literal ring must hold `newlits` more literals next to those of every round the consumer may still be
   // working on (rounds >= synced): takes more empty[] phases while that helps; false if they cannot fit at all
   BGX_DEV bool wait_lit_room(uint32_t newlits) {
+#ifdef BGX_HANDOVER_SYNCTHREADS
+    // lock step: while round rnd is produced the consumer works on round rnd - 1; everything older is consumed
+    return (lit_tail - (rnd ? sm->ctl.phead[(rnd - 1u) & (kQ - 1u)] : lit_head_p)) + newlits <= kLitQ;
+#endif
     uint32_t head_known = synced == rnd ? lit_head_p : sm->ctl.phead[synced & (kQ - 1u)];
     bool fits = (lit_tail - head_known) + newlits <= kLitQ;
     while (!fits && synced < rnd) {
@@ -750,15 +764,23 @@ struct ProdCtx {
     const uint32_t q = rnd & (kQ - 1u);
     if (lane == 0) sm->ctl.phead[q] = lit_head_p;   // literal head at the start of this round
     sm->rb[q].cmd[lane] = make_uint2(dxv, pkv);
-    warp_arrive(full_a + 8u * q, lane);
+    hand_over(q);
     ++rnd;
+  }
+  BGX_DEV void hand_over(uint32_t q) {
+#ifdef BGX_HANDOVER_SYNCTHREADS
+    (void)q;
+    __syncthreads();
+#else
+    warp_arrive(full_a + 8u * q, lane);
+#endif
   }
   // ends the page with an error: the slot of round `rnd` (free: every caller has acquired it) carries the abort flag
   BGX_DEV void publish_abort(uint32_t err) {
     const uint32_t q = rnd & (kQ - 1u);
     if (err && lane == 0) sm->ctl.err = err;
     sm->rb[q].cmd[lane] = make_uint2(0u, kPkAbort);
-    warp_arrive(full_a + 8u * q, lane);
+    hand_over(q);
   }
 };
 
@@ -915,7 +937,7 @@ BGX_DEV void producer_warp(const PageJob& job, WarpSmem* sm) {
     uint32_t len;
     const uint32_t sym = huff_decode<kCmdLutBits>(sm->lut_cmd, sm->aux[0], sm->sorted_cmd, bgx::kNumCmdSymbols, pk, len);
     const uint32_t sent = __ballot_sync(kFull, sym == (uint32_t)bgx::kCmdSentinel);
-    const uint32_t n = sent ? (uint32_t)(__ffs((int)sent) - 1) : 32u;   // commands in this round
+    const uint32_t n = umin32((uint32_t)__ffs((int)sent) - 1u, 32u);       // commands in this round (no sentinel: ffs = 0)
     pdone = sent != 0;
     const bool act = lane < n;
     const bool has_copy = sym < (uint32_t)bgx::kCmdSentinel;            // else insert-only (PageDecoder.cpp:308-317)
@@ -1081,7 +1103,8 @@ BGX_DEV void producer_warp(const PageJob& job, WarpSmem* sm) {
     const uint32_t need = round_ins > avail ? round_ins - avail : 0u;
     const uint32_t mult = n ? (n == 32u ? (need + 31u) >> 5 : cold_udiv(need + n - 1u, n)) : 0u;   // (n < 32: last round only)
     const uint32_t rl = n * mult;                     // literals the stream carries for this round
-    uint32_t mine = rl > lane ? (rl - lane + 31u) >> 5 : 0u;   // literal indices lit_tail + j*32 + lane
+    // literal indices lit_tail + j*32 + lane (lit_tail is a multiple of 32 until the last round)
+    uint32_t mine = n == 32u ? mult : (rl > lane ? (rl - lane + 31u) >> 5 : 0u);
     {
       // every command is validated here, so the consumer only ever sees rounds it can execute blindly: the page
       // must hold the round, and a match must start inside the page (PageDecoder.cpp:222-232 trusts both)
@@ -1140,14 +1163,19 @@ BGX_DEV void consumer_warp(const PageJob& job, WarpSmem* sm) {
   const saddr_t full_a = sb + (uint32_t)offsetof(WarpSmem, mbar), empty_a = full_a + 8u * kQ;
   const saddr_t ring_a = sb + (uint32_t)offsetof(WarpSmem, ring), litq_a = sb + (uint32_t)offsetof(WarpSmem, litq);
   const saddr_t tab_a = sb + (uint32_t)offsetof(WarpSmem, scratch), rb_a = sb + (uint32_t)offsetof(WarpSmem, rb);
-  const saddr_t tab2_a = tab_a + 128u;
+  const saddr_t tab2_a = tab_a + 128u, tab3_a = tab_a + 640u;
+  const uint32_t lane4 = pinned(4u * lane);
 
   for (uint32_t r = 0;; ++r) {
     const uint32_t q = r & (kQ - 1u);
+#ifdef BGX_HANDOVER_SYNCTHREADS
+    __syncthreads();
+#else
     if (!mbar_wait(full_a + 8u * q, (r / kQ) & 1u)) {   // the producer stopped publishing
       if (lane == 0) sm->ctl.err = kPageErrHang;
       break;
     }
+#endif
     const uint2 cw = lds_u32x2(rb_a + (uint32_t)sizeof(RoundBuf) * q + 8u * lane);
     if (cw.y & kPkAbort) break;
     const uint32_t dist = cw.x;                        // resolved and validated by the producer
@@ -1196,7 +1224,11 @@ BGX_DEV void consumer_warp(const PageJob& job, WarpSmem* sm) {
           sts_u8(ring_at(ring_a, base + t), lds_u8(litq_at(litq_a, lit_head + t)));
       }
     }
+#ifdef BGX_HANDOVER_SYNCTHREADS
+    __syncwarp();
+#else
     warp_arrive(empty_a + 8u * q, lane);   // the RoundBuf and this round's literals are no longer needed
+#endif
     // ---- copies. Wave 1: every copy whose source already is final, i.e. lies below the destination of the first
     //      copy of the round (or is that copy), flattened over 4-byte PIECES: lane t moves piece t of the wave
     //      (perfectly balanced, any length mix). Ready copies are compacted into tab2[]; a per-chunk bit mask of
@@ -1216,11 +1248,13 @@ BGX_DEV void consumer_warp(const PageJob& job, WarpSmem* sm) {
       const uint32_t S1 = E1 - np1;
       const uint32_t m1 = __ballot_sync(kFull, ready1);
       pending &= ~m1;
-      // wave-1 entry: (dst - 4 * first piece index, distance | (end - that) << 17); page <= 128 KiB, round <= kRoundMax
-      if (ready1) sts_u32x2(tab2_a + 8u * __popc(m1 & lt_mask), o_cpy - 4u * S1, dist | ((4u * S1 + cpy) << 17));
+      // wave-1 entry: (dst, source, end of the copy) relative to 4 * first piece index, so that piece t of the wave only
+      // adds 4 t to the first two and subtracts it from the third
+      if (ready1) sts_u32x4(tab2_a + 16u * __popc(m1 & lt_mask), o_cpy - 4u * S1, o_cpy - dist - 4u * S1, 4u * S1 + cpy, 0u);
       // the others, in command order: dst - round start (< 1024) | length (<= 1024) << 10 | distance (< 1024) << 21.
-      // A copy that is not in wave 1 overlaps itself or reads bytes of this round, so its distance is < kRoundMax.
-      else if (cpy) sts_u32(tab_a + 4u * __popc(pending & lt_mask), (o_cpy - pos) | (cpy << 10) | (dist << 21));
+      // A copy that is not in wave 1 overlaps itself or reads bytes of this round, so its distance is < kRoundMax and
+      // its source lies in the ring.
+      else if (cpy) sts_u32(tab3_a + 4u * __popc(pending & lt_mask), (o_cpy - pos) | (cpy << 10) | (dist << 21));
       __syncwarp();
       const uint32_t cidx = S1 >> 5;
       const uint32_t cbit = ready1 ? (1u << (S1 & 31u)) : 0u;
@@ -1228,62 +1262,68 @@ BGX_DEV void consumer_warp(const PageJob& job, WarpSmem* sm) {
       uint32_t before = 0;
 #pragma unroll 1
       for (uint32_t c0 = 0; 32u * c0 < T1; c0 += kPieceBatch) {
-        uint32_t w0[kPieceBatch], w1[kPieceBatch], meta[kPieceBatch];
+        uint32_t w0[kPieceBatch], w1[kPieceBatch], dd[kPieceBatch], sr[kPieceBatch];
 #pragma unroll
         for (int u = 0; u < kPieceBatch; ++u) {
           const uint32_t c = c0 + (uint32_t)u;
-          meta[u] = 0; w0[u] = 0; w1[u] = 0;
+          sr[u] = 0;
           if (32u * c < T1) {                                           // (uniform)
-            const uint32_t t4 = 128u * c + 4u * lane;
+            const uint32_t t4 = 128u * c + lane4;
             const uint32_t M = __reduce_or_sync(kFull, cidx == c ? cbit : 0u);
             uint32_t ord = before + __popc(M & le_mask) - 1u;
             before += __popc(M);
             ord = ord < last ? ord : last;                              // lanes past the end read a valid entry
-            const uint2 e = lds_u32x2(tab2_a + 8u * ord);
-            const uint32_t d = e.x + t4;                                // destination of this piece
-            const uint32_t sp = d - (e.y & 0x1ffffu);                   // its source
-            int32_t rem = (int32_t)((e.y >> 17) - t4);                  // bytes of the copy from this piece on (<= 0 past the end)
+            const uint4 e = lds_u32x4(tab2_a + 16u * ord);
+            dd[u] = e.x + t4;                                           // destination of this piece
+            const uint32_t sp = e.y + t4;                               // its source
+            int32_t rem = (int32_t)(e.z - t4);                          // bytes of the copy from this piece on (<= 0 past the end)
             rem = rem > 4 ? 4 : rem;
             if (rem > 0) {
               if ((int32_t)sp >= ring_lo) {
+#ifdef BGX_STRICT_LOADS   // (verification build: only the bytes of the piece are read, so that racecheck sees no overlap)
+                uint32_t v4 = 0;
+                for (int k = 0; k < rem; ++k) v4 |= lds_u8(ring_at(ring_a, sp + (uint32_t)k)) << (8 * k);
+                w0[u] = v4 << ((sp & 3u) * 8u);
+                w1[u] = (sp & 3u) ? v4 >> (32u - (sp & 3u) * 8u) : 0u;
+#else
                 w0[u] = lds_u32(ring_at(ring_a, sp & ~3u));
                 w1[u] = lds_u32(ring_at(ring_a, (sp & ~3u) + 4u));
+#endif
               } else {
                 const uint32_t* g = reinterpret_cast<const uint32_t*>(outb + (sp & ~3u));
                 w0[u] = ldg_u32(g);
                 w1[u] = ldg_u32(g + 1);
               }
-              meta[u] = ((sp & 3u) << 3) | ((uint32_t)rem << 5) | ((d & (kRing - 1u)) << 8);
+              sr[u] = ((sp & 3u) << 3) | ((uint32_t)rem << 5);
             }
           }
         }
 #pragma unroll
         for (int u = 0; u < kPieceBatch; ++u) {
-          const uint32_t m = meta[u];
+          const uint32_t m = sr[u];
           const uint32_t v = __funnelshift_r(w0[u], w1[u], m);          // (shift = low five bits = 8 * (source & 3))
-          const uint32_t dd = m >> 8;                                    // ring offset of the piece's first byte
-          if (m & (7u << 5)) sts_u8(ring_a + dd, v);
-          if (m & (6u << 5)) sts_u8(ring_at(ring_a, dd + 1u), v >> 8);   // rem >= 2
-          if ((m & (7u << 5)) >= (3u << 5)) sts_u8(ring_at(ring_a, dd + 2u), v >> 16);
-          if (m & (4u << 5)) sts_u8(ring_at(ring_a, dd + 3u), v >> 24);  // rem == 4
+          if (m & (7u << 5)) sts_u8(ring_at(ring_a, dd[u]), v);
+          if (m & (6u << 5)) sts_u8(ring_at(ring_a, dd[u] + 1u), v >> 8);   // rem >= 2
+          if (m >= (3u << 5)) sts_u8(ring_at(ring_a, dd[u] + 2u), v >> 16);
+          if (m & (4u << 5)) sts_u8(ring_at(ring_a, dd[u] + 3u), v >> 24);  // rem == 4
         }
       }
       __syncwarp();
       //    The remaining copies (they read bytes of this round's copies, or overlap themselves): in command order,
       //    each by the whole warp (lane j moves byte j; almost always a single step). In-order execution satisfies
       //    every dependency; an overlapping copy (dist < len) repeats its `dist`-byte pattern exactly as the
-      //    byte-serial reference loop does (PageDecoder.cpp:222-232). Their sources lie inside the ring.
+      //    byte-serial reference loop does (PageDecoder.cpp:222-232).
       const uint32_t npend = __popc(pending);
       if (npend) {
-        uint32_t e = lds_u32(tab_a);
+        uint32_t e = lds_u32(tab3_a);
 #pragma unroll 1
         for (uint32_t i = 0; i < npend; ++i) {
-          const uint32_t e_next = lds_u32(tab_a + 4u * (i + 1u < npend ? i + 1u : i));
+          const uint32_t e_next = lds_u32(tab3_a + 4u * (i + 1u < npend ? i + 1u : i));
           const uint32_t o_k = pos + (e & 1023u), n_k = (e >> 10) & 2047u, d_k = e >> 21;
           BGX_STAT(emu_stats().wavefronts++; emu_stats().sum_max_cpy += n_k);
           if (n_k <= 32u && d_k >= n_k) {                                  // the usual case: one step, no overlap
             if (lane < n_k) sts_u8(ring_at(ring_a, o_k + lane), lds_u8(ring_at(ring_a, o_k - d_k + lane)));
-          } else {                                                         // long or overlapping
+          } else {
 #pragma unroll 1
             for (uint32_t j = lane; j < n_k; j += 32) {
               const uint32_t mj = j < d_k ? j : j % d_k;
@@ -1483,7 +1523,7 @@ BGX_DEV void copy_page_warp(uint8_t* dst, const uint8_t* src, uint32_t n) {
     }
     for (; v < nv; v += 32) d[v] = s[v];
     i = nv << 4;
-#if BGX_RAW_PATH == 1
+#if BGX_RAW_PATH >= 1
   } else if (((a & 15u) == 0) && ((b & 7u) == 0)) {
     // typical stream layout: page data sits 8 bytes off a 16-byte boundary (8-byte header + 4n-byte table):
     // two 8-byte loads per 16-byte store, 8 stores in flight per lane
