@@ -29,3 +29,9 @@ ncu --set full --clock-control none --import-source on -k regex:bgx_de -s 2 -c 2
 compute-sanitizer --tool memcheck python scripts/gpu_sanity_small.py 2>&1 | tail -4 > ${O}_sanitizer_memcheck.log
 compute-sanitizer --tool synccheck python scripts/gpu_sanity_small.py 2>&1 | tail -4 > ${O}_sanitizer_synccheck.log
 cat ${O}_pytest.log; tail -c 400 ${O}_bench_n1.json; tail -3 ${O}_sweep.log
+# lock-step verification build under racecheck (every hand-over a CTA barrier, piece loads byte-exact): the hazards of the
+# production build that are ordered by mbarriers or are discarded over-reads must all disappear
+if [ -f build/variants/libbgx_sync.so ]; then
+  BGX_CUDA_LIB=$PWD/build/variants/libbgx_sync.so timeout 900 compute-sanitizer --tool racecheck --racecheck-report all python scripts/gpu_sanity_small.py 2>&1 | tail -6 > ${O}_sanitizer_racecheck_lockstep.log
+fi
+timeout 900 compute-sanitizer --tool racecheck --racecheck-report all python scripts/gpu_sanity_small.py 2>&1 | grep -E "RACECHECK SUMMARY|SANITY" > ${O}_sanitizer_racecheck_production.log

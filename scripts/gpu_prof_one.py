@@ -33,4 +33,5 @@ for _ in range(launches):
     e0.record(ts); plan.launch(ts.cuda_stream); e1.record(ts); torch.cuda.synchronize()
     print(kind, "ms", e0.elapsed_time(e1), "GB/s out", len(data) * copies / e0.elapsed_time(e1) / 1e6)
 assert plan.finish() == 0
+print("algorithmic_bytes", (len(s) + len(data)) * copies, "compressed", len(s), "uncompressed", len(data), "copies", copies)
 print("verify", bool(np.array_equal(keep[-1][1].cpu().numpy(), data)))
