@@ -18,6 +18,9 @@ c_u8p = ctypes.POINTER(ctypes.c_uint8)
 c_u32p = ctypes.POINTER(ctypes.c_uint32)
 
 
+PROGRESS_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32)   # bgx_progress_fn
+
+
 class BgxStream(ctypes.Structure):
     """mirror of bgx_stream (include/brotlig_b200.h)"""
     _fields_ = [
@@ -81,6 +84,12 @@ def cuda_lib() -> ctypes.CDLL:
         lib.bgx_decode_batch_host.argtypes = [vp, ctypes.c_uint32, ctypes.POINTER(vp), c_u32p, ctypes.POINTER(vp), c_u32p,
                                               ctypes.POINTER(ctypes.c_double)]
         lib.bgx_decode_batch_host.restype = ctypes.c_int
+        lib.bgx_decode_batch_host_multi.argtypes = [ctypes.POINTER(vp), ctypes.c_uint32, ctypes.c_uint32, ctypes.POINTER(vp), c_u32p,
+                                                    ctypes.POINTER(vp), c_u32p, ctypes.POINTER(ctypes.c_double)]
+        lib.bgx_decode_batch_host_multi.restype = ctypes.c_int
+        lib.bgx_decode_host_progress.argtypes = [vp, ctypes.c_uint32, vp, c_u32p, vp, ctypes.POINTER(ctypes.c_double), PROGRESS_FN, vp,
+                                                 ctypes.c_uint32]
+        lib.bgx_decode_host_progress.restype = ctypes.c_int
         lib.bgx_plan_create.argtypes = [vp, ctypes.POINTER(BgxStream), ctypes.c_uint32, ctypes.POINTER(vp)]
         lib.bgx_plan_create.restype = ctypes.c_int
         lib.bgx_plan_launch.argtypes = [vp, vp, vp]

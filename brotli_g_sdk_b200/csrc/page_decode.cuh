@@ -206,12 +206,6 @@ BGX_DEV saddr_t litq_at(saddr_t litq_a, uint32_t g) { return litq_a + (g & (kLit
 BGX_DEV void cp_async16(saddr_t smem_dst, const void* gmem_src) {
 #ifdef BGX_EMULATED
   memcpy(reinterpret_cast<void*>(smem_dst), gmem_src, 16);
-#elif defined(BGX_L2_EVICT_FIRST)
-  // EXPERIMENT: the compressed input is read exactly once -- ask L2 to drop it first, so that the pages' own output (the
-  // source of far matches) stays resident
-  uint64_t pol;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;\n" ::"r"(smem_dst), "l"(gmem_src), "l"(pol) : "memory");
 #else
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_dst), "l"(gmem_src) : "memory");
 #endif

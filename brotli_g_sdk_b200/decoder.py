@@ -14,7 +14,7 @@ from typing import Callable, Sequence
 
 import numpy as np
 
-from ._native import BgxPlanInfo, BgxStream, cuda_lib
+from ._native import PROGRESS_FN, BgxPlanInfo, BgxStream, cuda_lib
 
 BROTLIG_OK = 0
 BROTLIG_ABORTED = 1
@@ -122,6 +122,22 @@ class BrotligDecoder:
             raise BrotligError(rc, self.last_error())
         return [o[: out_sizes[i]] for i, o in enumerate(outputs)], float(ms.value)
 
+    def decode_host_progress(self, src, progress: Callable[[int, int], bool], output: np.ndarray | None = None,
+                             pages_per_group: int = 0) -> tuple[np.ndarray, float]:
+        """bgx_decode_host_progress: progress(page, num_pages) is called for every page after its group of pages was
+        decoded; a true return stops the decode (the rest of the output is zero), as BrotligDecoder.cpp:318-325."""
+        s = _u8(src)
+        if output is None:
+            output = np.empty(DecompressedSize(s), dtype=np.uint8)
+        osz = ctypes.c_uint32(output.size)
+        ms = ctypes.c_double(0.0)
+        cb = PROGRESS_FN(lambda user, page, pages: 1 if progress(int(page), int(pages)) else 0)
+        rc = cuda_lib().bgx_decode_host_progress(self._ctx, s.size, s.ctypes.data, ctypes.byref(osz), output.ctypes.data, ctypes.byref(ms),
+                                                 cb, None, pages_per_group)
+        if rc:
+            raise BrotligError(rc, self.last_error())
+        return output[: osz.value], float(ms.value)
+
     # ---- device-resident
     def plan(self, streams: Sequence[dict]) -> Plan:
         """streams: dicts with d_src (int device pointer), src_size, src_capacity, d_dst, dst_capacity,
@@ -143,6 +159,26 @@ class BrotligDecoder:
         if rc:
             raise BrotligError(rc, self.last_error())
         return Plan(self, handle, arr)
+
+
+def decode_batch_host_multi(decoders: Sequence[BrotligDecoder], srcs: Sequence, outputs: Sequence[np.ndarray] | None = None):
+    """bgx_decode_batch_host_multi: one process, one decoder per device; whole streams are assigned to the decoders
+    (balanced by compressed size) and decoded concurrently. Returns (outputs, kernel ms of the slowest device)."""
+    lib = cuda_lib()
+    ins = [_u8(s) for s in srcs]
+    n = len(ins)
+    if outputs is None:
+        outputs = [np.empty(DecompressedSize(s), dtype=np.uint8) for s in ins]
+    ctxs = (ctypes.c_void_p * len(decoders))(*[d._ctx for d in decoders])
+    in_ptrs = (ctypes.c_void_p * n)(*[a.ctypes.data for a in ins])
+    in_sizes = (ctypes.c_uint32 * n)(*[a.size for a in ins])
+    out_ptrs = (ctypes.c_void_p * n)(*[o.ctypes.data for o in outputs])
+    out_sizes = (ctypes.c_uint32 * n)(*[o.size for o in outputs])
+    ms = ctypes.c_double(0.0)
+    rc = lib.bgx_decode_batch_host_multi(ctxs, len(decoders), n, in_ptrs, in_sizes, out_ptrs, out_sizes, ctypes.byref(ms))
+    if rc:
+        raise BrotligError(rc, "; ".join(d.last_error() for d in decoders))
+    return [o[: out_sizes[i]] for i, o in enumerate(outputs)], float(ms.value)
 
 
 _default: BrotligDecoder | None = None

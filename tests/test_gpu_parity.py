@@ -260,3 +260,38 @@ def test_cli_round_trip(tmp_path, sdk):
     assert r.returncode == 0, r.stderr
     assert "GB/s decompressed" in r.stdout
     assert np.array_equal(np.fromfile(out, dtype=np.uint8), data)
+
+
+def test_progress_callback_and_abort_through_the_c_abi(sdk, oracle, dec):
+    """bgx_decode_host_progress: one report per page, in order; a true return stops the decode between two page groups and
+    leaves zeros behind (BrotligDecoder.cpp:318-325,448)"""
+    from brotli_g_sdk_b200 import datagen
+    data = np.concatenate([datagen.text_like(21 * 65536, seed=71), datagen.structured_binary(11 * 65536 + 500, seed=72)])
+    s = sdk.Encode(data)
+    want = oracle.decode(s)
+    seen = []
+    out, ms = dec.decode_host_progress(s, lambda p, n: seen.append((p, n)) or False, pages_per_group=8)
+    assert np.array_equal(out, want) and ms > 0
+    assert seen == [(p, 33) for p in range(33)]
+    seen.clear()
+    out, _ = dec.decode_host_progress(s, lambda p, n: seen.append(p) or p >= 9, output=np.full(len(data), 0xA5, np.uint8), pages_per_group=8)
+    assert seen == list(range(10))                       # stopped inside the second group of 8 pages
+    assert np.array_equal(out[: 16 * 65536], want[: 16 * 65536]) and not out[16 * 65536:].any()
+
+
+def test_batch_over_several_contexts(sdk, oracle):
+    """bgx_decode_batch_host_multi: whole streams split over the contexts (one per device; on a one-GPU box two contexts of
+    the same device), outputs identical to the oracle"""
+    import torch
+    from brotli_g_sdk_b200 import datagen
+    from brotli_g_sdk_b200.decoder import decode_batch_host_multi
+    ndev = max(1, torch.cuda.device_count())
+    decs = [sdk.BrotligDecoder(i % ndev) for i in range(max(2, min(ndev, 4)))]
+    datas = [datagen.mixed(n, seed=80 + i) for i, n in enumerate((300000, 65536, 1 << 20, 70000, 5, 2 * 65536 + 1, 650000))]
+    streams = [sdk.Encode(d) for d in datas]
+    outs, ms = decode_batch_host_multi(decs, streams)
+    for d, s, o in zip(datas, streams, outs):
+        assert np.array_equal(o, oracle.decode(s)) and np.array_equal(o, d)
+    assert ms > 0
+    for d in decs:
+        d.close()
