@@ -63,8 +63,10 @@ inline void plan_stream_segments(uint32_t i, const uint8_t* input, uint32_t inpu
     const size_t lo = up_prev > table_end ? up_prev : table_end;   // corrupt tables stay in bounds and in order
     if (up1 < lo) up1 = lo;
     if (up1 > input_size) up1 = input_size;
-    const size_t dn0 = (size_t)pb * si.page_size;
-    const size_t dn1 = last ? (size_t)si.uncompressed_size : (size_t)(pb + pc) * si.page_size;
+    size_t dn0 = (size_t)pb * si.page_size;
+    size_t dn1 = last ? (size_t)si.uncompressed_size : (size_t)(pb + pc) * si.page_size;
+    if (dn1 > si.uncompressed_size) dn1 = si.uncompressed_size;   // (parse_stream_header rejects sizes that wrap; belt and braces)
+    if (dn0 > dn1) dn0 = dn1;
     seg.push_back(HostSegment{i, pb, pc, up_prev, up1, dn0, dn1});
     up_prev = up1;
   }
