@@ -53,7 +53,8 @@ __global__ void __launch_bounds__(kPageThreads, BGX_CTAS_PER_SM) bgx_decode_page
                                                                         uint32_t q_begin, uint32_t q_end, QueueCtl* ctl,
                                                                         uint32_t* __restrict__ page_status) {
   __shared__ bgxk::WarpSmem sm;
-  __shared__ uint32_t q_shared;
+  uint32_t& q_shared = sm.q_shared;
+  const bool layout_ok = bgxk::arena_layout_ok(sm.ring, sm.litq);
   const uint32_t tid = threadIdx.x;
   uint32_t cur_stream = 0;   // owner of the last page this CTA decoded (streams are in queue order)
   bool first_compressed = true;   // the page arena's mbarriers have not been initialised yet
@@ -106,6 +107,8 @@ __global__ void __launch_bounds__(kPageThreads, BGX_CTAS_PER_SM) bgx_decode_page
       bgxk::copy_page_cta(out, in, e.out_size, &sm);
     } else if (e.in_size < 8u || (e.in_off & 3u) != 0u) {
       status = bgxk::kPageErrTable;
+    } else if (!layout_ok) {
+      status = bgxk::kPageErrLayout;
     } else {
       bgxk::PageJob job;
       job.in = in;

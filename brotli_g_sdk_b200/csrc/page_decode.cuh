@@ -100,6 +100,7 @@ enum : uint32_t {
   kPageErrLiterals = 4,     // a round needs more literals than it carries
   kPageErrTable = 8,        // malformed prefix-code description
   kPageErrHang = 16,        // the two warps of the page stopped handing rounds over (cannot happen on a valid stream)
+  kPageErrLayout = 32,      // the shared-memory arena is not where this build expects it (never on a supported toolchain)
 };
 
 struct HuffAux {
@@ -123,7 +124,14 @@ struct PageCtl {             // hand-over state of the two warps of a page
 };
 
 struct WarpSmem {
-  uint16_t lut_cmd[1 << kCmdLutBits];
+  // The first three members are placed so that the output ring sits on a 2048-byte and the literal ring on a 512-byte
+  // boundary of the shared-memory WINDOW (static shared memory of a CTA starts 0x400 into its window on sm_90+), which
+  // turns "base + (position & mask)" into one LOP3 ((position & mask) | base) everywhere. bgx_decode_pages_kernel checks
+  // the two addresses once and refuses to decode (kPageErrLayout) if a toolchain ever lays the arena out differently.
+  uint16_t lut_cmd[1 << kCmdLutBits];   // 1024 B
+  uint8_t ring[kRing];              // output ring; while tables are read: code lengths [0..727] and the
+                                    // 512 x u16 code-length-code LUT [1024..2047]
+  uint8_t litq[kLitQ];              // literal ring, indexed by page-global literal index
   uint16_t lut_lit[1 << kLitLutBits];
   uint16_t lut_dist[1 << kDistLutBits];
   uint16_t sorted_cmd[bgx::kNumCmdSymbols];
@@ -131,16 +139,15 @@ struct WarpSmem {
   uint8_t sorted_lit[bgx::kNumLitSymbols];
   HuffAux aux[3];
   uint32_t lenlut[48];              // [0..23] insert code, [24..47] copy code: base | extra_bits << 16
-  alignas(16) uint32_t scratch[192]; // table build: cnt[16], next[16], 18 code-length-code lengths;
-                                    // consumer: [0..31] insert table, [32..159] wave-1 copies (uint4), [160..191] the other copies
-  uint8_t litq[kLitQ];              // literal ring, indexed by page-global literal index
-  alignas(16) uint8_t ring[kRing];  // output ring; while tables are read: code lengths [0..727] and the
-                                    // 512 x u16 code-length-code LUT [1024..2047]
+  alignas(16) uint32_t scratch[224]; // table build: cnt[16], next[16], 18 code-length-code lengths;
+                                    // consumer: [0..31] insert table, [32..159] wave-1 copies (uint4), [160..223] the other copies (two words each)
   alignas(16) uint4 stage[32][4];   // compressed-input staging: per lane 4 slots x 16 B (cp.async ring)
   RoundBuf rb[kQ];
   alignas(8) uint64_t mbar[2 * kQ];   // full[kQ], empty[kQ]
   PageCtl ctl;
+  uint32_t q_shared;                // the CTA's current slot of the page queue (bgx_decode_pages_kernel)
 };
+static_assert(offsetof(WarpSmem, ring) == 1024 && offsetof(WarpSmem, litq) == 3072, "ring / literal ring placement (see above)");
 
 // ---------------------------------------------------------------------------------------------
 // Explicit shared-state-space accesses. A `saddr_t` is a 32-bit shared-window address on the device (so
@@ -186,8 +193,21 @@ BGX_DEV uint32_t pinned(uint32_t v) {
   return v;
 }
 // byte p of the output ring / literal index g of the literal ring
+#ifdef BGX_EMULATED
 BGX_DEV saddr_t ring_at(saddr_t ring_a, uint32_t p) { return ring_a + (p & (kRing - 1u)); }
 BGX_DEV saddr_t litq_at(saddr_t litq_a, uint32_t g) { return litq_a + (g & (kLitQ - 1u)); }
+#else   // the rings are aligned to their size in the shared window (WarpSmem): OR instead of ADD, one LOP3
+BGX_DEV saddr_t ring_at(saddr_t ring_a, uint32_t p) { return ring_a | (p & (kRing - 1u)); }
+BGX_DEV saddr_t litq_at(saddr_t litq_a, uint32_t g) { return litq_a | (g & (kLitQ - 1u)); }
+#endif
+BGX_DEV bool arena_layout_ok(const void* ring, const void* litq) {
+#ifdef BGX_EMULATED
+  (void)ring; (void)litq;
+  return true;
+#else
+  return (((uint32_t)__cvta_generic_to_shared(ring)) & (kRing - 1u)) == 0u && (((uint32_t)__cvta_generic_to_shared(litq)) & (kLitQ - 1u)) == 0u;
+#endif
+}
 
 // ---------------------------------------------------------------------------------------------
 // Input staging + bit reader. Every lane reads its own sub-stream strictly sequentially, so the
@@ -1134,6 +1154,7 @@ BGX_DEV void producer_warp(const PageJob& job, WarpSmem* sm) {
   }
 }
 
+
 // ------------------------------------------------------------------------------------- CONSUMER
 // rare paths of the consumer, out of line
 BGX_COLD void cold_flush_bytes(const WarpSmem* sm, uint8_t* out, uint32_t from, uint32_t to, uint32_t zero_to, uint32_t lane) {
@@ -1251,10 +1272,15 @@ BGX_DEV void consumer_warp(const PageJob& job, WarpSmem* sm) {
       // wave-1 entry: (dst, source, end of the copy) relative to 4 * first piece index, so that piece t of the wave only
       // adds 4 t to the first two and subtracts it from the third
       if (ready1) sts_u32x4(tab2_a + 16u * __popc(m1 & lt_mask), o_cpy - 4u * S1, o_cpy - dist - 4u * S1, 4u * S1 + cpy, 0u);
-      // the others, in command order: dst - round start (< 1024) | length (<= 1024) << 10 | distance (< 1024) << 21.
-      // A copy that is not in wave 1 overlaps itself or reads bytes of this round, so its distance is < kRoundMax and
-      // its source lies in the ring.
-      else if (cpy) sts_u32(tab3_a + 4u * __popc(pending & lt_mask), (o_cpy - pos) | (cpy << 10) | (dist << 21));
+      // the others, in command order: ring offset of dst | ring offset of source << 11 | length << 22 (63: not a
+      // single step), and for those a second word: dst - round start (< 1024) | length (<= 1024) << 10 | distance
+      // (< 1024) << 21. A copy that is not in wave 1 overlaps itself or reads bytes of this round, so its distance is
+      // < kRoundMax and its source lies in the ring.
+      else if (cpy) {
+        const uint32_t slot = 4u * __popc(pending & lt_mask);
+        sts_u32(tab3_a + slot, (o_cpy & (kRing - 1u)) | (((o_cpy - dist) & (kRing - 1u)) << 11) | ((cpy <= 32u && dist >= cpy ? cpy : 63u) << 22));
+        sts_u32(tab3_a + 128u + slot, (o_cpy - pos) | (cpy << 10) | (dist << 21));   // for the long / overlapping ones
+      }
       __syncwarp();
       const uint32_t cidx = S1 >> 5;
       const uint32_t cbit = ready1 ? (1u << (S1 & 31u)) : 0u;
@@ -1314,25 +1340,24 @@ BGX_DEV void consumer_warp(const PageJob& job, WarpSmem* sm) {
       //    every dependency; an overlapping copy (dist < len) repeats its `dist`-byte pattern exactly as the
       //    byte-serial reference loop does (PageDecoder.cpp:222-232).
       const uint32_t npend = __popc(pending);
-      if (npend) {
-        uint32_t e = lds_u32(tab3_a);
 #pragma unroll 1
-        for (uint32_t i = 0; i < npend; ++i) {
-          const uint32_t e_next = lds_u32(tab3_a + 4u * (i + 1u < npend ? i + 1u : i));
+      for (uint32_t i = 0; i < npend;) {
+        const uint32_t a = lds_u32(tab3_a + 4u * i);
+        const uint32_t n_s = a >> 22;
+        BGX_STAT(emu_stats().wavefronts++; emu_stats().sum_max_cpy += n_s);
+        if (n_s <= 32u) {                                                // the usual case: one step, no overlap
+          if (lane < n_s) sts_u8(ring_at(ring_a, a + lane), lds_u8(ring_at(ring_a, (a >> 11) + lane)));
+        } else {                                                         // long or overlapping
+          const uint32_t e = lds_u32(tab3_a + 128u + 4u * i);
           const uint32_t o_k = pos + (e & 1023u), n_k = (e >> 10) & 2047u, d_k = e >> 21;
-          BGX_STAT(emu_stats().wavefronts++; emu_stats().sum_max_cpy += n_k);
-          if (n_k <= 32u && d_k >= n_k) {                                  // the usual case: one step, no overlap
-            if (lane < n_k) sts_u8(ring_at(ring_a, o_k + lane), lds_u8(ring_at(ring_a, o_k - d_k + lane)));
-          } else {
 #pragma unroll 1
-            for (uint32_t j = lane; j < n_k; j += 32) {
-              const uint32_t mj = j < d_k ? j : j % d_k;
-              sts_u8(ring_at(ring_a, o_k + j), lds_u8(ring_at(ring_a, o_k - d_k + mj)));
-            }
+          for (uint32_t j = lane; j < n_k; j += 32) {
+            const uint32_t mj = j < d_k ? j : j % d_k;
+            sts_u8(ring_at(ring_a, o_k + j), lds_u8(ring_at(ring_a, o_k - d_k + mj)));
           }
-          __syncwarp();
-          e = e_next;
         }
+        __syncwarp();
+        ++i;
       }
     }
     pos = round_end;
