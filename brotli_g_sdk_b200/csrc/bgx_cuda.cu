@@ -50,8 +50,8 @@ constexpr int kPageThreads = 64;   // two warps per page: producer (entropy deco
 #define BGX_CTAS_PER_SM 16
 #endif
 __global__ void __launch_bounds__(kPageThreads, BGX_CTAS_PER_SM) bgx_decode_pages_kernel(const StreamDev* __restrict__ streams, uint32_t nstreams,
-                                                                        uint32_t q_begin, uint32_t q_end, QueueCtl* ctl,
-                                                                        uint32_t* __restrict__ page_status) {
+                                                                        uint32_t q_begin, uint32_t q_end, float q_to_stream,
+                                                                        QueueCtl* ctl, uint32_t* __restrict__ page_status) {
   __shared__ bgxk::WarpSmem sm;
   uint32_t& q_shared = sm.q_shared;
   const bool layout_ok = bgxk::arena_layout_ok(sm.ring, sm.litq);
@@ -71,6 +71,17 @@ __global__ void __launch_bounds__(kPageThreads, BGX_CTAS_PER_SM) bgx_decode_page
     if (lo + 1 < nstreams && streams[lo + 1].first_q <= q) {
       ++lo;
       uint32_t hi = nstreams;
+      // batches of many small streams: a proportional guess (exact when the streams hold equal numbers of pages)
+      // brackets the owner with two independent loads, so the search below rarely runs
+      uint32_t g = (uint32_t)((float)q * q_to_stream);
+      g = g < nstreams - 1u ? g : nstreams - 1u;
+      const uint32_t fg = streams[g].first_q, fg1 = g + 1 < nstreams ? streams[g + 1].first_q : 0xffffffffu;
+      if (fg <= q) {
+        lo = g > lo ? g : lo;
+        if (fg1 > q) hi = g + 1u;
+      } else {
+        hi = g;
+      }
       while (hi - lo > 1) {
         const uint32_t mid = (lo + hi) >> 1;
         if (streams[mid].first_q <= q) lo = mid; else hi = mid;
@@ -492,7 +503,8 @@ static int launch_range(bgx_context* ctx, bgx_plan* plan, uint32_t a, uint32_t b
   if (q1 > q0) {
     const uint64_t max_blocks = (uint64_t)ctx->sm_count * ctx->blocks_per_sm;
     const uint32_t grid = (uint32_t)std::min<uint64_t>(max_blocks, q1 - q0);
-    bgx_decode_pages_kernel<<<grid, kPageThreads, 0, st>>>(plan->d_streams, (uint32_t)plan->h_streams.size(), q0, q1,
+    const float q_to_stream = (float)plan->h_streams.size() / (float)std::max<uint32_t>(plan->total_pages, 1u);
+    bgx_decode_pages_kernel<<<grid, kPageThreads, 0, st>>>(plan->d_streams, (uint32_t)plan->h_streams.size(), q0, q1, q_to_stream,
                                                  plan->d_ctl + group, plan->d_status);
     BGX_CUDA(ctx, cudaGetLastError());
   }

@@ -414,44 +414,64 @@ BGX_DEV uint32_t huff_decode(const uint16_t* lut, const HuffAux& aux, const Sort
 }
 
 // ---------------------------------------------------------------------------------------------
+// Table construction. It runs once per table and page, so it is written for SIZE: one out-of-line routine serves the
+// three tables (LUT width, alphabet and the element size of `sorted` are run-time values), which keeps a page's table phase
+// inside the instruction cache next to the round loops of the other pages on the SM.
+struct TableRef {
+  uint16_t* lut;
+  HuffAux* aux;
+  void* sorted;            // uint16_t[alphabet], or uint8_t[alphabet] when sorted_u8
+  uint32_t bits;           // LUT index width
+  uint32_t alphabet;
+  uint32_t sorted_u8;
+};
+
 // cooperative fill of the LUT entries owned by one code: all indices whose low `len` bits equal
 // `rev` (the bit-reversed code).
-template <int BITS>
-BGX_DEV void lut_fill_coop(uint16_t* lut, uint32_t rev, uint32_t len, uint16_t entry, uint32_t lane) {
-  for (uint32_t j = rev + (lane << len); j < (1u << BITS); j += (32u << len)) lut[j] = entry;
+BGX_DEV void lut_fill_coop(uint16_t* lut, uint32_t bits, uint32_t rev, uint32_t len, uint16_t entry, uint32_t lane) {
+#pragma unroll 1
+  for (uint32_t j = rev + (lane << len); j < (1u << bits); j += (32u << len)) lut[j] = entry;
 }
 
 // Builds LUT + canonical arrays from the code lengths in `lens[0..n)` (shared memory).
 // Canonical order = (length, symbol index), as GenerateHuffmanTable (BrotligHuffmanTable.cpp:44-71).
-template <int BITS, typename SortedT>
-BGX_DEV uint32_t build_table(WarpSmem* sm, const uint8_t* lens, uint32_t n, uint16_t* lut, HuffAux& aux, SortedT* sorted,
-                             uint32_t lane) {
+BGX_DEV uint32_t build_table(WarpSmem* sm, const uint8_t* lens, const TableRef& t, uint32_t lane) {
+  const uint32_t n = t.alphabet, bits = t.bits;
+  uint16_t* const lut = t.lut;
+  HuffAux& aux = *t.aux;
   uint32_t* cnt = sm->scratch;        // [16]
   uint32_t* next = sm->scratch + 16;  // [16] running position in `sorted` per length; [0]: the code is usable
   if (lane < 16) cnt[lane] = 0;
   __syncwarp();
-  for (uint32_t s = lane; s < n; s += 32) atomicAdd(&cnt[lens[s]], 1u);
+#pragma unroll 1
+  for (uint32_t s = lane; s < n; s += 32) {
+    const uint32_t L = lens[s];
+    if (L) atomicAdd(&cnt[L], 1u);
+  }
   __syncwarp();
-  if (lane == 0) {
-    uint32_t code = 0, off = 0, kraft = 0;
-    cnt[0] = 0;
-    aux.limit[0] = 0;
-    aux.base[0] = 0;
-    for (uint32_t L = 1; L <= 15; ++L) {
-      code = (code + cnt[L - 1]) << 1;                   // first code of length L
-      aux.base[L] = (uint16_t)(off - code);
-      const uint32_t lim = (code + cnt[L]) << (15 - L);
-      aux.limit[L] = (uint16_t)(lim > 0x8000u ? 0x8000u : lim);
+  {
+    // Lane L (1..15) owns length L. With the counts left-aligned to 15 bits, the first code of a length is the
+    // EXCLUSIVE prefix sum over the shorter lengths (code[L] = (code[L-1] + cnt[L-1]) << 1, left-aligned), its limit the
+    // inclusive one, and the total the Kraft sum: one 64-bit warp scan (left-aligned counts | plain counts) gives all.
+    const uint32_t L = lane;
+    const uint32_t sh = 15u - (L & 15u);
+    const uint32_t c = (L >= 1u && L <= 15u) ? cnt[L] : 0u;
+    const uint64_t both = warp_incl_scan64(((uint64_t)(c << sh) << 32) | c, lane);
+    const uint32_t lim = (uint32_t)(both >> 32), off = (uint32_t)both - c;
+    const uint32_t code = (lim - (c << sh)) >> sh;       // first code of length L
+    if (L <= 15u) {
+      aux.base[L] = (uint16_t)(L ? off - code : 0u);
+      aux.limit[L] = (uint16_t)(L ? (lim > 0x8000u ? 0x8000u : lim) : 0u);
       next[L] = off;
-      off += cnt[L];
-      kraft += cnt[L] << (15 - L);
     }
     // A prefix code must be complete (Kraft sum exactly 1; RFC 7932 section 3.2), or consist of a single symbol. The
     // reference trusts the lengths (BrotligHuffmanTable.cpp:44-71,135-145): an over-subscribed set overwrites table
     // entries, an incomplete one leaves entries of the previous page in place. Both are rejected here.
-    next[0] = (kraft == 0x8000u || off == 1u) ? 0u : 1u;
+    __syncwarp();
+    if (lane == 15u) next[0] = (lim == 0x8000u || (uint32_t)both == 1u) ? 0u : 1u;
   }
   __syncwarp();
+#pragma unroll 1
   for (uint32_t s0 = 0; s0 < n; s0 += 32) {
     const uint32_t s = s0 + lane;
     const uint32_t L = s < n ? lens[s] : 0u;
@@ -466,25 +486,29 @@ BGX_DEV uint32_t build_table(WarpSmem* sm, const uint8_t* lens, uint32_t n, uint
     __syncwarp();
     if (L && rank == 0) next[L] += __popc(m);
     if (L) {
-      if (idx < n) sorted[idx] = (SortedT)s;
-      if (L > (uint32_t)BITS) {
-        const uint32_t prefix = code >> (L - BITS);
-        lut[__brev(prefix) >> (32 - BITS)] = kLongCode;
+      if (idx < n) {
+        if (t.sorted_u8) static_cast<uint8_t*>(t.sorted)[idx] = (uint8_t)s;
+        else static_cast<uint16_t*>(t.sorted)[idx] = (uint16_t)s;
+      }
+      if (L > bits) {
+        const uint32_t prefix = code >> (L - bits);
+        lut[__brev(prefix) >> (32u - bits)] = kLongCode;
       }
     }
     // codes owning >= 32 LUT entries: whole warp fills them, one code at a time
-    uint32_t wide = __ballot_sync(kFull, L != 0 && L + 5 <= (uint32_t)BITS);
+    uint32_t wide = __ballot_sync(kFull, L != 0 && L + 5 <= bits);
     while (wide) {
       const int k = __ffs(wide) - 1;
       wide &= wide - 1;
       const uint32_t Lk = __shfl_sync(kFull, L, k);
       const uint32_t ck = __shfl_sync(kFull, code, k);
-      lut_fill_coop<BITS>(lut, __brev(ck) >> (32 - Lk), Lk, (uint16_t)((s0 + k) | (Lk << 10)), lane);
+      lut_fill_coop(lut, bits, __brev(ck) >> (32 - Lk), Lk, (uint16_t)((s0 + k) | (Lk << 10)), lane);
     }
     // the rest: each lane fills its own (<= 16) entries
-    if (L + 5 > (uint32_t)BITS && L <= (uint32_t)BITS) {
+    if (L + 5 > bits && L <= bits) {
       const uint16_t entry = (uint16_t)(s | (L << 10));
-      for (uint32_t j = __brev(code) >> (32 - L); j < (1u << BITS); j += (1u << L)) lut[j] = entry;
+#pragma unroll 1
+      for (uint32_t j = __brev(code) >> (32 - L); j < (1u << bits); j += (1u << L)) lut[j] = entry;
     }
     __syncwarp();
   }
@@ -495,48 +519,51 @@ BGX_DEV uint32_t build_table(WarpSmem* sm, const uint8_t* lens, uint32_t n, uint
 
 // Reads one prefix-code description (trivial / simple / complex) and builds its tables.
 // Returns 0 or kPageErrTable. Cursor conventions: every table starts at sub-stream 0 (lane 0).
-template <int BITS, typename SortedT>
-BGX_DEV uint32_t load_table(WarpSmem* sm, BitRd& rd, PageIn& in, uint32_t alphabet, uint16_t* lut, HuffAux& aux,
-                            SortedT* sorted, uint32_t lane) {
+BGX_DEV uint32_t load_table(WarpSmem* sm, BitRd& rd, PageIn& in, const TableRef& t, uint32_t lane) {
+  const uint32_t alphabet = t.alphabet, bits = t.bits;
+  uint16_t* const lut = t.lut;
   const uint32_t max_bits = bgx::bit_length(alphabet - 1);
   br_topup(rd, in);
   uint32_t hdr = 0;
   if (lane == 0) hdr = br_read(rd, in, 6);
   hdr = __shfl_sync(kFull, hdr, 0);
   const uint32_t type = hdr & 3u;
-  if (type == 0) {  // trivial: one symbol, zero-length code (BrotligHuffmanTable.cpp:87-101)
-    uint32_t sym = 0;
-    if (lane == 0) sym = br_read(rd, in, max_bits);
-    sym = __shfl_sync(kFull, sym, 0);
-    for (uint32_t j = lane; j < (1u << BITS); j += 32) lut[j] = (uint16_t)sym;   // length field 0
-    __syncwarp();
-    return 0;
-  }
-  if (type == 1) {  // simple: 2..4 symbols, k-th symbol in sub-stream k, table filled in STORED order (:102-125)
-    const uint32_t nsym = ((hdr >> 2) & 3u) + 1u;
+  if (type < 2u) {
+    // trivial: one symbol, zero-length code (BrotligHuffmanTable.cpp:87-101);
+    // simple: 2..4 symbols, k-th symbol in sub-stream k, table filled in STORED order (:102-125)
+    const uint32_t nsym = type ? ((hdr >> 2) & 3u) + 1u : 1u;
     const uint32_t tree_select = (hdr >> 4) & 1u;
-    if (nsym < 2) return kPageErrTable;
+    if (type && nsym < 2) return kPageErrTable;
     uint32_t sym = 0;
     if (lane < nsym) sym = br_read(rd, in, max_bits);
+    if (!type) {
+      sym = __shfl_sync(kFull, sym, 0);
+#pragma unroll 1
+      for (uint32_t j = lane; j < (1u << bits); j += 32) lut[j] = (uint16_t)sym;   // length field 0
+      __syncwarp();
+      return 0;
+    }
     // shapes {1,1} {1,2,2} {2,2,2,2} {1,2,3,3}; codes are consecutive in stored order
     const uint32_t shape = nsym < 4 ? nsym - 2 : (tree_select ? 3u : 2u);
     const uint32_t lens4 = shape == 0 ? 0x0011u : shape == 1 ? 0x0221u : shape == 2 ? 0x2222u : 0x3321u;
     const uint32_t codes4 = shape == 0 ? 0x0010u : shape == 1 ? 0x0320u : shape == 2 ? 0x3210u : 0x7620u;
+#pragma unroll 1
     for (uint32_t k = 0; k < nsym; ++k) {
       const uint32_t sk = __shfl_sync(kFull, sym, k);
       const uint32_t Lk = (lens4 >> (4 * k)) & 15u;
       const uint32_t ck = (codes4 >> (4 * k)) & 15u;
-      lut_fill_coop<BITS>(lut, __brev(ck) >> (32 - Lk), Lk, (uint16_t)((sk & 0x3ffu) | (Lk << 10)), lane);
+      lut_fill_coop(lut, bits, __brev(ck) >> (32 - Lk), Lk, (uint16_t)((sk & 0x3ffu) | (Lk << 10)), lane);
     }
     __syncwarp();
     return 0;
   }
   if (type != 2) return kPageErrTable;
 
-  // ---- complex (:126-200). 1) code-length code: i-th 5-bit length in sub-stream i, storage order below.
+  // ---- complex (:126-200). 1) code-length code: i-th 5-bit length in sub-stream i, storage order
+  //      1,2,3,4,0,5,17,6,16,7,8,9,10,11,12,13,14,15 (lane i reads the length of symbol kOrder[i])
   const uint32_t ncl = ((hdr >> 2) & 15u) + 4u;
-  // order packed 5 bits each: 1,2,3,4,0,5,17,6,16,7,8,9,10,11,12,13,14,15
-  const uint32_t kOrder[18] = {1, 2, 3, 4, 0, 5, 17, 6, 16, 7, 8, 9, 10, 11, 12, 13, 14, 15};
+  const uint32_t my_sym = lane < 4u ? lane + 1u : lane == 4u ? 0u : lane == 5u ? 5u : lane == 6u ? 17u : lane == 7u ? 6u :
+                          lane == 8u ? 16u : lane - 2u;
   uint32_t* cl_len_by_sym = sm->scratch + 16;   // [18] (next[] is not live yet)
   uint16_t* cl_lut = reinterpret_cast<uint16_t*>(sm->ring + 1024);   // 512 entries: sym | len << 8 (lens[] uses ring[0..727])
   uint32_t myread = 0;
@@ -544,7 +571,7 @@ BGX_DEV uint32_t load_table(WarpSmem* sm, BitRd& rd, PageIn& in, uint32_t alphab
   __syncwarp();
   if (lane < ncl && lane < 18) {
     myread = br_read(rd, in, 5);
-    cl_len_by_sym[kOrder[lane]] = myread;
+    cl_len_by_sym[my_sym] = myread;
   }
   const uint32_t bad = __ballot_sync(kFull, myread > 9u);
   if (bad) return kPageErrTable;   // reference: out-of-bounds table index
@@ -561,23 +588,27 @@ BGX_DEV uint32_t load_table(WarpSmem* sm, BitRd& rd, PageIn& in, uint32_t alphab
   const uint32_t msame = __match_any_sync(kFull, ls);
   const uint32_t rank = __popc(msame & ((1u << lane) - 1u));
   uint32_t code = 0, mycode = 0, prevcnt = 0;
+#pragma unroll 1
   for (uint32_t L = 1; L <= 9; ++L) {
     code = (code + prevcnt) << 1;
     prevcnt = __popc(__ballot_sync(kFull, lane < ncl && lane < 18 && myread == L));
     if (ls == L) mycode = code + rank;
   }
+#pragma unroll 1
   for (uint32_t j = lane; j < 256; j += 32) reinterpret_cast<uint32_t*>(cl_lut)[j] = 0;   // sym 0, len 0
   __syncwarp();
+#pragma unroll 1
   for (uint32_t k = 0; k < 18; ++k) {
     const uint32_t Lk = __shfl_sync(kFull, ls, k);
     const uint32_t ck = __shfl_sync(kFull, mycode, k);
-    if (Lk) lut_fill_coop<9>(cl_lut, (__brev(ck) >> (32 - Lk)) & 511u, Lk, (uint16_t)(k | (Lk << 8)), lane);
+    if (Lk) lut_fill_coop(cl_lut, 9u, (__brev(ck) >> (32 - Lk)) & 511u, Lk, (uint16_t)(k | (Lk << 8)), lane);
   }
   __syncwarp();
 
   // ---- 2) the code lengths themselves: k-th code-length symbol lives in sub-stream k mod 32
   uint8_t* lens = sm->ring;
   uint32_t filled = 0, prev_carry = bgx::kInitialRepeatLen;
+#pragma unroll 1
   while (filled < alphabet) {
     br_topup(rd, in);
     const uint32_t pk = br_peek(rd);
@@ -595,6 +626,7 @@ BGX_DEV uint32_t load_table(WarpSmem* sm, BitRd& rd, PageIn& in, uint32_t alphab
     const uint32_t prevval = below ? pv : prev_carry;
     const uint32_t val = s == (uint32_t)bgx::kRepeatPrev ? prevval : (s == (uint32_t)bgx::kRepeatZero ? 0u : s);
     if (active) {
+#pragma unroll 1
       for (uint32_t k = 0; k < run && start + k < alphabet; ++k) lens[start + k] = (uint8_t)val;
       br_skip(rd, in, nb);
     }
@@ -603,7 +635,30 @@ BGX_DEV uint32_t load_table(WarpSmem* sm, BitRd& rd, PageIn& in, uint32_t alphab
     filled += __reduce_add_sync(kFull, active ? run : 0u);
   }
   __syncwarp();
-  return build_table<BITS, SortedT>(sm, lens, alphabet, lut, aux, sorted, lane);
+  return build_table(sm, lens, t, lane);
+}
+
+// The three prefix codes of a page -- insert&copy (728 symbols), distance (544), literal (256), in stream order
+// (PageDecoder.cpp:126-147) -- read and built by ONE out-of-line routine working on copies of the reader state.
+struct TableIo { BitRd rd; PageIn in; };
+BGX_COLD uint32_t load_tables(WarpSmem* sm, TableIo* io, uint32_t lane) {
+  BitRd rd = io->rd;
+  PageIn in = io->in;
+  uint32_t terr = 0;
+#pragma unroll 1
+  for (uint32_t k = 0; k < 3u && !terr; ++k) {
+    TableRef t;
+    t.lut = k == 0 ? sm->lut_cmd : k == 1 ? sm->lut_dist : sm->lut_lit;
+    t.aux = &sm->aux[k];
+    t.sorted = k == 0 ? static_cast<void*>(sm->sorted_cmd) : k == 1 ? static_cast<void*>(sm->sorted_dist) : static_cast<void*>(sm->sorted_lit);
+    t.bits = k == 0 ? (uint32_t)kCmdLutBits : k == 1 ? (uint32_t)kDistLutBits : (uint32_t)kLitLutBits;
+    t.alphabet = k == 0 ? (uint32_t)bgx::kNumCmdSymbols : k == 1 ? (uint32_t)bgx::kNumDistSymbols : (uint32_t)bgx::kNumLitSymbols;
+    t.sorted_u8 = k == 2 ? 1u : 0u;
+    terr = load_table(sm, rd, in, t, lane);
+  }
+  io->rd = rd;
+  io->in = in;
+  return terr;
 }
 
 
@@ -697,21 +752,31 @@ BGX_DEV void mbar_arrive(saddr_t a) {
   asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(a) : "memory");
 #endif
 }
-// Waits for the phase with this parity to complete. Returns false when it did not within kWaitLimitCycles (about a
+// Waits for the phase with this parity to complete. Returns false when it did not within kMaxPolls polls (about a
 // second): a hand-over that a valid stream cannot produce. Both warps of the page then leave with kPageErrHang, so a
 // corrupt stream can never hang the persistent kernel (the emulator's dead-lock detection plays this role on the CPU).
 #ifndef BGX_WAIT_HINT_NS
 #define BGX_WAIT_HINT_NS 0x989680
 #endif
-constexpr long long kWaitLimitCycles = 2000000000ll;
+#ifndef BGX_WAIT_FAST_POLLS
+#define BGX_WAIT_FAST_POLLS 1024
+#endif
+#ifndef BGX_WAIT_SLEEP_NS
+#define BGX_WAIT_SLEEP_NS 128
+#endif
+constexpr uint32_t kFastPolls = BGX_WAIT_FAST_POLLS;   // polls before the waiting warp starts to sleep between polls
+constexpr uint32_t kMaxPolls = 1u << 23;               // sleeping polls before a wait is declared hung (about a second)
 BGX_DEV bool mbar_wait(saddr_t a, uint32_t parity) {
 #ifdef BGX_EMULATED
   wemu::mbar_wait(reinterpret_cast<uint64_t*>(a), parity);
   return true;
 #else
-  // try_wait suspends the warp until the phase completes or a (hardware-bounded) time limit passes
-  uint32_t done;
-  long long t0 = 0;
+  // try_wait comes back after a short, hardware-bounded time whatever limit it is given (measured: ~20 cycles per
+  // poll). Hand-overs between rounds take a few polls and must be seen at once (sleeping from the 16th poll on costs
+  // structured binary 2.5 % and 16 KiB pages 5 %); only a warp that has polled kFastPolls times (~10 us: the consumer
+  // during a table phase, or a page that hangs) sleeps between polls. The poll count doubles as the hang guard
+  // (kMaxPolls sleeping polls are far beyond any wait of a valid stream).
+  uint32_t done, polls = 0;
   for (;;) {
 #if BGX_WAIT_HINT_NS > 0
     asm volatile(
@@ -725,9 +790,10 @@ BGX_DEV bool mbar_wait(saddr_t a, uint32_t parity) {
         "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(a), "r"(parity) : "memory");
 #endif
     if (done) return true;
-    const long long now = clock64();
-    if (t0 == 0) t0 = now;
-    else if (now - t0 > kWaitLimitCycles) return false;
+    if (++polls > kFastPolls) {
+      if (polls > kMaxPolls) return false;
+      __nanosleep(BGX_WAIT_SLEEP_NS);
+    }
   }
 #endif
 }
@@ -924,10 +990,14 @@ BGX_DEV void producer_warp(const PageJob& job, WarpSmem* sm) {
   }
   br_init(rd, in, sub_off);
   __syncwarp();
-  // ---- the three prefix codes: insert&copy (728), distance (544), literal (256)  (PageDecoder.cpp:126-147)
-  uint32_t terr = load_table<kCmdLutBits>(sm, rd, in, bgx::kNumCmdSymbols, sm->lut_cmd, sm->aux[0], sm->sorted_cmd, lane);
-  if (!terr) terr = load_table<kDistLutBits>(sm, rd, in, bgx::kNumDistSymbols, sm->lut_dist, sm->aux[1], sm->sorted_dist, lane);
-  if (!terr) terr = load_table<kLitLutBits>(sm, rd, in, bgx::kNumLitSymbols, sm->lut_lit, sm->aux[2], sm->sorted_lit, lane);
+  // ---- the three prefix codes (load_tables)
+  uint32_t terr;
+  {
+    TableIo io;
+    io.rd = rd; io.in = in;
+    terr = load_tables(sm, &io, lane);
+    rd = io.rd; in = io.in;
+  }
   __syncwarp();
 
   ProdCtx pc;
@@ -1158,7 +1228,9 @@ BGX_DEV void producer_warp(const PageJob& job, WarpSmem* sm) {
 // ------------------------------------------------------------------------------------- CONSUMER
 // rare paths of the consumer, out of line
 BGX_COLD void cold_flush_bytes(const WarpSmem* sm, uint8_t* out, uint32_t from, uint32_t to, uint32_t zero_to, uint32_t lane) {
+#pragma unroll 1
   for (uint32_t p = from + lane; p < to; p += 32) out[p] = sm->ring[p & (kRing - 1)];
+#pragma unroll 1
   for (uint32_t z = to + lane; z < zero_to; z += 32) out[z] = 0;
 }
 // Positions are kept in "v-space": v = page offset + skew, skew = (output address & 15), so that v % 16 == 0 is
@@ -1530,7 +1602,8 @@ BGX_DEV void decondition_block_fast(const bgx::PreconLayout& L, uint32_t t, cons
 
 // ---------------------------------------------------------------------------------------------
 // raw page (compressed size == uncompressed size, PageDecoder.cpp:70-76): a straight copy.
-BGX_DEV void copy_page_warp(uint8_t* dst, const uint8_t* src, uint32_t n) {
+// (out of line: ONE copy of the unrolled loops in the kernel, outside the address range of the round loops)
+BGX_COLD void copy_page_warp(uint8_t* dst, const uint8_t* src, uint32_t n) {
   const uint32_t lane = lane_id();
   const uintptr_t a = reinterpret_cast<uintptr_t>(dst), b = reinterpret_cast<uintptr_t>(src);
   uint32_t i = 0;
@@ -1546,6 +1619,7 @@ BGX_DEV void copy_page_warp(uint8_t* dst, const uint8_t* src, uint32_t n) {
 #pragma unroll
       for (int u = 0; u < 8; ++u) d[v + u * 32] = t[u];
     }
+#pragma unroll 1
     for (; v < nv; v += 32) d[v] = s[v];
     i = nv << 4;
 #if BGX_RAW_PATH >= 1
@@ -1567,6 +1641,7 @@ BGX_DEV void copy_page_warp(uint8_t* dst, const uint8_t* src, uint32_t n) {
         d[v + u * 32] = w;
       }
     }
+#pragma unroll 1
     for (; v < nv; v += 32) {
       const uint2 lo = s[2 * v], hi = s[2 * v + 1];
       uint4 w;
@@ -1589,6 +1664,7 @@ BGX_DEV void copy_page_warp(uint8_t* dst, const uint8_t* src, uint32_t n) {
 #pragma unroll
       for (int u = 0; u < 16; ++u) d[v + u * 32] = t[u];
     }
+#pragma unroll 1
     for (; v < nv; v += 32) d[v] = s[v];
     i = nv << 3;
 #endif
@@ -1604,9 +1680,11 @@ BGX_DEV void copy_page_warp(uint8_t* dst, const uint8_t* src, uint32_t n) {
 #pragma unroll
       for (int u = 0; u < 4; ++u) d[v + u * 32] = t[u];
     }
+#pragma unroll 1
     for (; v < nv; v += 32) d[v] = s[v];
     i = nv << 2;
   }
+#pragma unroll 1
   for (uint32_t j = i + lane; j < n; j += 32) dst[j] = src[j];
 }
 

@@ -35,3 +35,5 @@ if [ -f build/variants/libbgx_sync.so ]; then
   BGX_CUDA_LIB=$PWD/build/variants/libbgx_sync.so timeout 900 compute-sanitizer --tool racecheck --racecheck-report all python scripts/gpu_sanity_small.py 2>&1 | tail -6 > ${O}_sanitizer_racecheck_lockstep.log
 fi
 timeout 900 compute-sanitizer --tool racecheck --racecheck-report all python scripts/gpu_sanity_small.py 2>&1 | grep -E "RACECHECK SUMMARY|SANITY" > ${O}_sanitizer_racecheck_production.log
+# where a 4 KiB page spends its time: one --set full capture of the 4 KiB single-page-stream launch
+SWEEP_SINGLE=1 timeout 900 ncu --set full --clock-control none --import-source on -k regex:bgx_decode_pages -c 1 -f -o ${O}_page4k python scripts/page_size_sweep.py 1024 mixed 4096 > ${O}_ncu_page4k.log 2>&1

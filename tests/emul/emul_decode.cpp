@@ -106,7 +106,8 @@ uint32_t emul_table_status(const uint8_t* lens, uint32_t n) {
   memcpy(sm->ring, lens, n);
   uint32_t st[32];
   wemu::run_warp([&] {
-    st[wemu::lane()] = bgxk::build_table<bgxk::kCmdLutBits, uint16_t>(sm, sm->ring, n, sm->lut_cmd, sm->aux[0], sm->sorted_cmd, (uint32_t)wemu::lane());
+    bgxk::TableRef t{sm->lut_cmd, &sm->aux[0], sm->sorted_cmd, (uint32_t)bgxk::kCmdLutBits, (uint32_t)n, 0u};
+    st[wemu::lane()] = bgxk::build_table(sm, sm->ring, t, (uint32_t)wemu::lane());
   });
   uint32_t r = st[0];
   for (int l = 1; l < 32; ++l)
