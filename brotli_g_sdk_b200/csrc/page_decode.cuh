@@ -129,8 +129,8 @@ struct WarpSmem {
   // turns "base + (position & mask)" into one LOP3 ((position & mask) | base) everywhere. bgx_decode_pages_kernel checks
   // the two addresses once and refuses to decode (kPageErrLayout) if a toolchain ever lays the arena out differently.
   uint16_t lut_cmd[1 << kCmdLutBits];   // 1024 B
-  uint8_t ring[kRing];              // output ring; while tables are read: code lengths [0..727] and the
-                                    // 512 x u16 code-length-code LUT [1024..2047]
+  uint8_t ring[kRing];              // output ring; while tables are read: the list of used symbols (u16 each) and,
+                                    // unless that list may need the room, the 512 x u16 code-length-code LUT
   uint8_t litq[kLitQ];              // literal ring, indexed by page-global literal index
   uint16_t lut_lit[1 << kLitLutBits];
   uint16_t lut_dist[1 << kDistLutBits];
@@ -148,6 +148,8 @@ struct WarpSmem {
   uint32_t q_shared;                // the CTA's current slot of the page queue (bgx_decode_pages_kernel)
 };
 static_assert(offsetof(WarpSmem, ring) == 1024 && offsetof(WarpSmem, litq) == 3072, "ring / literal ring placement (see above)");
+static_assert(kRing >= 2 * bgx::kNumCmdSymbols && kRing >= 1024 + 1024 && 2 * bgx::kNumLitSymbols <= 1024 && (1 << kLitLutBits) >= 512,
+              "table phase: the list of used symbols fits the ring, the code-length-code LUT its upper half or the literal LUT");
 
 // ---------------------------------------------------------------------------------------------
 // Explicit shared-state-space accesses. A `saddr_t` is a 32-bit shared-window address on the device (so
@@ -433,93 +435,86 @@ BGX_DEV void lut_fill_coop(uint16_t* lut, uint32_t bits, uint32_t rev, uint32_t 
   for (uint32_t j = rev + (lane << len); j < (1u << bits); j += (32u << len)) lut[j] = entry;
 }
 
-// Builds LUT + canonical arrays from the code lengths in `lens[0..n)` (shared memory).
-// Canonical order = (length, symbol index), as GenerateHuffmanTable (BrotligHuffmanTable.cpp:44-71).
-BGX_DEV uint32_t build_table(WarpSmem* sm, const uint8_t* lens, const TableRef& t, uint32_t lane) {
-  const uint32_t n = t.alphabet, bits = t.bits;
+// Builds LUT + canonical arrays of one prefix code from
+//   list[0..used)  (symbol | length << 10) of every symbol with a non-zero length, in symbol order (shared memory)
+//   sm->scratch[0..15]  the number of symbols per length
+// Canonical order = (length, symbol index), as GenerateHuffmanTable (BrotligHuffmanTable.cpp:44-71). Work is
+// proportional to the symbols in use and to the LUT size, not to the alphabet (most of the 728 / 544 symbols of a
+// page are unused):
+//   1. one 64-bit warp scan over the lengths gives first codes, limits, offsets into `sorted` and the Kraft sum;
+//   2. `sorted`: 32 list entries at a time, rank within equal lengths by match_any;
+//   3. the LUT, filled by POSITION: in most-significant-bit-first order the codes of a canonical prefix code tile the
+//      code space in `sorted` order, so the entries of length L are the contiguous positions [lo_L, hi_L) and entry m
+//      of that range belongs to sorted[off_L + ((m - lo_L) >> (bits - L))]; lanes take consecutive positions (the
+//      LUT index is the bit-reversed position, the stream being read least-significant bit first).
+BGX_DEV uint32_t build_table(WarpSmem* sm, const uint16_t* list, uint32_t used, const TableRef& t, uint32_t lane) {
+  const uint32_t bits = t.bits;
   uint16_t* const lut = t.lut;
   HuffAux& aux = *t.aux;
-  uint32_t* cnt = sm->scratch;        // [16]
-  uint32_t* next = sm->scratch + 16;  // [16] running position in `sorted` per length; [0]: the code is usable
-  if (lane < 16) cnt[lane] = 0;
+  const uint32_t* cnt = sm->scratch;  // [16]
+  uint32_t* next = sm->scratch + 16;  // [16] running position in `sorted` per length
+  // ---- 1. lane L (1..15) owns length L. With the counts left-aligned to 15 bits, the first code of a length is the
+  //      EXCLUSIVE prefix sum over the shorter lengths (code[L] = (code[L-1] + cnt[L-1]) << 1, left-aligned), its limit
+  //      the inclusive one, and the total the Kraft sum.
+  const uint32_t sh = 15u - (lane & 15u);
+  const uint32_t c = (lane >= 1u && lane <= 15u) ? cnt[lane] : 0u;
+  const uint64_t both = warp_incl_scan64(((uint64_t)(c << sh) << 32) | c, lane);
+  const uint32_t lim = (uint32_t)(both >> 32), off = (uint32_t)both - c;
+  const uint32_t first_la = lim - (c << sh);             // first code of length L, left-aligned to 15 bits
   __syncwarp();
-#pragma unroll 1
-  for (uint32_t s = lane; s < n; s += 32) {
-    const uint32_t L = lens[s];
-    if (L) atomicAdd(&cnt[L], 1u);
+  if (lane <= 15u) {
+    aux.base[lane] = (uint16_t)(lane ? off - (first_la >> sh) : 0u);
+    aux.limit[lane] = (uint16_t)(lane ? (lim > 0x8000u ? 0x8000u : lim) : 0u);
+    next[lane] = off;
   }
+  // A prefix code must be complete (Kraft sum exactly 1; RFC 7932 section 3.2), or consist of a single symbol. The
+  // reference trusts the lengths (BrotligHuffmanTable.cpp:44-71,135-145): an over-subscribed set overwrites table
+  // entries, an incomplete one leaves entries of the previous page in place. Both are rejected here.
+  const uint32_t kraft = __shfl_sync(kFull, lim, 15);
   __syncwarp();
-  {
-    // Lane L (1..15) owns length L. With the counts left-aligned to 15 bits, the first code of a length is the
-    // EXCLUSIVE prefix sum over the shorter lengths (code[L] = (code[L-1] + cnt[L-1]) << 1, left-aligned), its limit the
-    // inclusive one, and the total the Kraft sum: one 64-bit warp scan (left-aligned counts | plain counts) gives all.
-    const uint32_t L = lane;
-    const uint32_t sh = 15u - (L & 15u);
-    const uint32_t c = (L >= 1u && L <= 15u) ? cnt[L] : 0u;
-    const uint64_t both = warp_incl_scan64(((uint64_t)(c << sh) << 32) | c, lane);
-    const uint32_t lim = (uint32_t)(both >> 32), off = (uint32_t)both - c;
-    const uint32_t code = (lim - (c << sh)) >> sh;       // first code of length L
-    if (L <= 15u) {
-      aux.base[L] = (uint16_t)(L ? off - code : 0u);
-      aux.limit[L] = (uint16_t)(L ? (lim > 0x8000u ? 0x8000u : lim) : 0u);
-      next[L] = off;
-    }
-    // A prefix code must be complete (Kraft sum exactly 1; RFC 7932 section 3.2), or consist of a single symbol. The
-    // reference trusts the lengths (BrotligHuffmanTable.cpp:44-71,135-145): an over-subscribed set overwrites table
-    // entries, an incomplete one leaves entries of the previous page in place. Both are rejected here.
-    __syncwarp();
-    if (lane == 15u) next[0] = (lim == 0x8000u || (uint32_t)both == 1u) ? 0u : 1u;
-  }
-  __syncwarp();
+  if (kraft != 0x8000u && used != 1u) return kPageErrTable;
+  // ---- 2. sorted
 #pragma unroll 1
-  for (uint32_t s0 = 0; s0 < n; s0 += 32) {
-    const uint32_t s = s0 + lane;
-    const uint32_t L = s < n ? lens[s] : 0u;
-    if (__ballot_sync(kFull, L != 0u) == 0u) continue;   // (most of the 728 / 544 symbols of a page are unused)
+  for (uint32_t i0 = 0; i0 < used; i0 += 32) {
+    const uint32_t i = i0 + lane;
+    const uint32_t e = i < used ? list[i] : 0u;
+    const uint32_t L = e >> 10;
     const uint32_t m = __match_any_sync(kFull, L);
     const uint32_t rank = __popc(m & ((1u << lane) - 1u));
-    uint32_t idx = 0, code = 0;
     if (L) {
-      idx = next[L] + rank;
-      code = (idx - aux.base[L]) & 0xffffu;
+      const uint32_t idx = next[L] + rank;               // (< used <= alphabet: the counts are those of the list)
+      if (t.sorted_u8) static_cast<uint8_t*>(t.sorted)[idx] = (uint8_t)e;
+      else static_cast<uint16_t*>(t.sorted)[idx] = (uint16_t)(e & 0x3ffu);
     }
     __syncwarp();
     if (L && rank == 0) next[L] += __popc(m);
-    if (L) {
-      if (idx < n) {
-        if (t.sorted_u8) static_cast<uint8_t*>(t.sorted)[idx] = (uint8_t)s;
-        else static_cast<uint16_t*>(t.sorted)[idx] = (uint16_t)s;
-      }
-      if (L > bits) {
-        const uint32_t prefix = code >> (L - bits);
-        lut[__brev(prefix) >> (32u - bits)] = kLongCode;
-      }
-    }
-    // codes owning >= 32 LUT entries: whole warp fills them, one code at a time
-    uint32_t wide = __ballot_sync(kFull, L != 0 && L + 5 <= bits);
-    while (wide) {
-      const int k = __ffs(wide) - 1;
-      wide &= wide - 1;
-      const uint32_t Lk = __shfl_sync(kFull, L, k);
-      const uint32_t ck = __shfl_sync(kFull, code, k);
-      lut_fill_coop(lut, bits, __brev(ck) >> (32 - Lk), Lk, (uint16_t)((s0 + k) | (Lk << 10)), lane);
-    }
-    // the rest: each lane fills its own (<= 16) entries
-    if (L + 5 > bits && L <= bits) {
-      const uint16_t entry = (uint16_t)(s | (L << 10));
-#pragma unroll 1
-      for (uint32_t j = __brev(code) >> (32 - L); j < (1u << bits); j += (1u << L)) lut[j] = entry;
-    }
     __syncwarp();
   }
-  const uint32_t unusable = next[0];
-  __syncwarp();   // (the next table's description reuses this scratch: every lane has read the flag before that)
-  return unusable ? kPageErrTable : 0u;
+  // ---- 3. the LUT by position
+  const uint32_t down = 15u - bits;
+  const uint32_t lo_mine = first_la >> down, hi_mine = (lim > 0x8000u ? 0x8000u : lim) >> down;
+#pragma unroll 1
+  for (uint32_t L = 1; L <= bits; ++L) {
+    const uint32_t lo = __shfl_sync(kFull, lo_mine, (int)L), hi = __shfl_sync(kFull, hi_mine, (int)L);
+    const uint32_t off_l = __shfl_sync(kFull, off, (int)L);
+    const uint32_t tag = L << 10, sh2 = bits - L;
+#pragma unroll 1
+    for (uint32_t m = lo + lane; m < hi; m += 32) {
+      const uint32_t idx = off_l + ((m - lo) >> sh2);
+      const uint32_t sym = t.sorted_u8 ? (uint32_t)static_cast<const uint8_t*>(t.sorted)[idx] : (uint32_t)static_cast<const uint16_t*>(t.sorted)[idx];
+      lut[__brev(m) >> (32u - bits)] = (uint16_t)(sym | tag);
+    }
+  }
+  // positions past the last code of <= bits bits start longer codes (a lone symbol: positions no valid stream reaches)
+#pragma unroll 1
+  for (uint32_t m = __shfl_sync(kFull, hi_mine, (int)bits) + lane; m < (1u << bits); m += 32) lut[__brev(m) >> (32u - bits)] = kLongCode;
+  __syncwarp();   // (the next table's description reuses the scratch and the list)
+  return 0u;
 }
 
 // Reads one prefix-code description (trivial / simple / complex) and builds its tables.
 // Returns 0 or kPageErrTable. Cursor conventions: every table starts at sub-stream 0 (lane 0).
-BGX_DEV uint32_t load_table(WarpSmem* sm, BitRd& rd, PageIn& in, const TableRef& t, uint32_t lane) {
+BGX_DEV uint32_t load_table(WarpSmem* sm, BitRd& rd, PageIn& in, const TableRef& t, uint16_t* cl_lut, uint32_t lane) {
   const uint32_t alphabet = t.alphabet, bits = t.bits;
   uint16_t* const lut = t.lut;
   const uint32_t max_bits = bgx::bit_length(alphabet - 1);
@@ -560,14 +555,15 @@ BGX_DEV uint32_t load_table(WarpSmem* sm, BitRd& rd, PageIn& in, const TableRef&
   if (type != 2) return kPageErrTable;
 
   // ---- complex (:126-200). 1) code-length code: i-th 5-bit length in sub-stream i, storage order
-  //      1,2,3,4,0,5,17,6,16,7,8,9,10,11,12,13,14,15 (lane i reads the length of symbol kOrder[i])
+  //      1,2,3,4,0,5,17,6,16,7,8,9,10,11,12,13,14,15 (lane i reads the length of symbol my_sym)
   const uint32_t ncl = ((hdr >> 2) & 15u) + 4u;
   const uint32_t my_sym = lane < 4u ? lane + 1u : lane == 4u ? 0u : lane == 5u ? 5u : lane == 6u ? 17u : lane == 7u ? 6u :
                           lane == 8u ? 16u : lane - 2u;
+  uint32_t* cnt = sm->scratch;                  // [16] symbols per length of the code being described (build_table)
   uint32_t* cl_len_by_sym = sm->scratch + 16;   // [18] (next[] is not live yet)
-  uint16_t* cl_lut = reinterpret_cast<uint16_t*>(sm->ring + 1024);   // 512 entries: sym | len << 8 (lens[] uses ring[0..727])
   uint32_t myread = 0;
   if (lane < 18) cl_len_by_sym[lane] = 0;   // the reference leaves these uninitialised when ncl < 18
+  if (lane < 16) cnt[lane] = 0;
   __syncwarp();
   if (lane < ncl && lane < 18) {
     myread = br_read(rd, in, 5);
@@ -575,39 +571,45 @@ BGX_DEV uint32_t load_table(WarpSmem* sm, BitRd& rd, PageIn& in, const TableRef&
   }
   const uint32_t bad = __ballot_sync(kFull, myread > 9u);
   if (bad) return kPageErrTable;   // reference: out-of-bounds table index
-  {
-    // the code-length code itself must be a complete prefix code or a single symbol (see build_table)
-    const uint32_t used = __ballot_sync(kFull, myread != 0u);
-    const uint32_t kraft = __reduce_add_sync(kFull, myread ? (512u >> myread) : 0u);
-    if (kraft != 512u && __popc(used) != 1) return kPageErrTable;
-  }
+  // the code-length code itself must be a complete prefix code or a single symbol (see build_table)
+  const uint32_t cl_used = __ballot_sync(kFull, myread != 0u);
+  const uint32_t cl_kraft = __reduce_add_sync(kFull, myread ? (512u >> myread) : 0u);
+  if (cl_kraft != 512u && __popc(cl_used) != 1) return kPageErrTable;
   __syncwarp();
-  // canonical codes over symbols 0..ncl-1 (GenerateHuffmanTable is called with size = ncl, :145),
-  // but the per-length counts come from every length that was read (:135-142)
-  const uint32_t ls = (lane < ncl && lane < 18) ? cl_len_by_sym[lane] : 0u;
-  const uint32_t msame = __match_any_sync(kFull, ls);
-  const uint32_t rank = __popc(msame & ((1u << lane) - 1u));
-  uint32_t code = 0, mycode = 0, prevcnt = 0;
-#pragma unroll 1
-  for (uint32_t L = 1; L <= 9; ++L) {
-    code = (code + prevcnt) << 1;
-    prevcnt = __popc(__ballot_sync(kFull, lane < ncl && lane < 18 && myread == L));
-    if (ls == L) mycode = code + rank;
-  }
-#pragma unroll 1
-  for (uint32_t j = lane; j < 256; j += 32) reinterpret_cast<uint32_t*>(cl_lut)[j] = 0;   // sym 0, len 0
-  __syncwarp();
+  // canonical codes over symbols 0..ncl-1 (GenerateHuffmanTable is called with size = ncl, :145), but the per-length
+  // counts come from every length that was read (:135-142): the code of symbol i, left-aligned to 9 bits, is the sum
+  // of 512 >> length over the lengths read for ANY symbol that are shorter, plus those of equal length among the
+  // symbols 0..ncl-1 below i.
+  const uint32_t ls = (lane < ncl && lane < 18) ? cl_len_by_sym[lane] : 0u;   // symbol `lane` of the canonical set
+  const uint32_t lr = lane < 18 ? cl_len_by_sym[lane] : 0u;                   // every length that was read
+  uint32_t code_la = 0;
 #pragma unroll 1
   for (uint32_t k = 0; k < 18; ++k) {
-    const uint32_t Lk = __shfl_sync(kFull, ls, k);
-    const uint32_t ck = __shfl_sync(kFull, mycode, k);
-    if (Lk) lut_fill_coop(cl_lut, 9u, (__brev(ck) >> (32 - Lk)) & 511u, Lk, (uint16_t)(k | (Lk << 8)), lane);
+    const uint32_t Lr = __shfl_sync(kFull, lr, (int)k), Lc = __shfl_sync(kFull, ls, (int)k);
+    if (Lr && Lr < ls) code_la += 512u >> Lr;
+    if (Lc && Lc == ls && k < lane) code_la += 512u >> Lc;
+  }
+#pragma unroll 1
+  for (uint32_t j = lane; j < 256; j += 32) reinterpret_cast<uint32_t*>(cl_lut)[j] = 0;   // sym 0, len 0 where no code lands
+  __syncwarp();
+  // LUT by position, as in build_table: symbol k owns the 512 >> L positions from its left-aligned code on
+#pragma unroll 1
+  for (uint32_t k = 0; k < 18; ++k) {
+    const uint32_t Lk = __shfl_sync(kFull, ls, (int)k);
+    const uint32_t lo = __shfl_sync(kFull, code_la, (int)k);
+    if (!Lk) continue;
+    const uint32_t hi = lo + (512u >> Lk);
+    const uint16_t entry = (uint16_t)(k | (Lk << 8));
+#pragma unroll 1
+    for (uint32_t m = lo + lane; m < hi && m < 512u; m += 32) cl_lut[__brev(m) >> 23] = entry;
   }
   __syncwarp();
 
-  // ---- 2) the code lengths themselves: k-th code-length symbol lives in sub-stream k mod 32
-  uint8_t* lens = sm->ring;
-  uint32_t filled = 0, prev_carry = bgx::kInitialRepeatLen;
+  // ---- 2) the code lengths themselves: k-th code-length symbol lives in sub-stream k mod 32. They are not stored as
+  //      an array of 728 lengths: every symbol with a non-zero length goes to a compact list (symbol | length << 10,
+  //      symbol order), and the lengths are counted on the way.
+  uint16_t* list = reinterpret_cast<uint16_t*>(sm->ring);
+  uint32_t filled = 0, used = 0, prev_carry = bgx::kInitialRepeatLen;
 #pragma unroll 1
   while (filled < alphabet) {
     br_topup(rd, in);
@@ -617,25 +619,35 @@ BGX_DEV uint32_t load_table(WarpSmem* sm, BitRd& rd, PageIn& in, const TableRef&
     uint32_t run = 1, nb = l;
     if (s == (uint32_t)bgx::kRepeatPrev) { run = 3 + ((pk >> l) & 3u); nb = l + 2; }
     else if (s == (uint32_t)bgx::kRepeatZero) { run = 3 + ((pk >> l) & 7u); nb = l + 3; }
-    const uint32_t incl = warp_incl_scan(run, lane);
-    const uint32_t start = filled + incl - run;
-    const bool active = start < alphabet;   // otherwise this symbol does not exist: consume nothing
-    const uint32_t expl = __ballot_sync(kFull, active && s < 16u);
+    // "repeat previous" repeats the last explicit length before it (the lanes past the end of the alphabet lie above
+    // every lane that counts, so they cannot be that one)
+    const uint32_t expl = __ballot_sync(kFull, s < 16u);
     const uint32_t below = expl & ((1u << lane) - 1u);
     const uint32_t pv = __shfl_sync(kFull, s, below ? (31 - __clz((int)below)) : 0);
     const uint32_t prevval = below ? pv : prev_carry;
     const uint32_t val = s == (uint32_t)bgx::kRepeatPrev ? prevval : (s == (uint32_t)bgx::kRepeatZero ? 0u : s);
-    if (active) {
+    // positions: symbols covered | list entries produced << 16, one scan
+    const uint32_t incl = warp_incl_scan(run | (val ? run << 16 : 0u), lane);
+    const uint32_t start = filled + (incl & 0xffffu) - run;
+    const bool active = start < alphabet;   // otherwise this symbol does not exist: consume nothing
+    const uint32_t run_c = active ? umin32(run, alphabet - start) : 0u;
+    const uint32_t nz = val ? run_c : 0u;
+    if (nz) {
+      const uint32_t pos = used + (incl >> 16) - run;
+      const uint32_t tag = val << 10;
 #pragma unroll 1
-      for (uint32_t k = 0; k < run && start + k < alphabet; ++k) lens[start + k] = (uint8_t)val;
-      br_skip(rd, in, nb);
+      for (uint32_t k = 0; k < nz; ++k) list[pos + k] = (uint16_t)((start + k) | tag);
+      atomicAdd(&cnt[val], nz);
     }
-    if (expl) prev_carry = __shfl_sync(kFull, s, 31 - __clz((int)expl));
+    if (active) br_skip(rd, in, nb);
+    const uint32_t expl_act = expl & __ballot_sync(kFull, active);
+    if (expl_act) prev_carry = __shfl_sync(kFull, s, 31 - __clz((int)expl_act));
     else (void)__shfl_sync(kFull, s, 0);
-    filled += __reduce_add_sync(kFull, active ? run : 0u);
+    filled += __shfl_sync(kFull, incl, 31) & 0xffffu;
+    used += __reduce_add_sync(kFull, nz);
   }
   __syncwarp();
-  return build_table(sm, lens, t, lane);
+  return build_table(sm, list, used, t, lane);
 }
 
 // The three prefix codes of a page -- insert&copy (728 symbols), distance (544), literal (256), in stream order
@@ -654,7 +666,11 @@ BGX_COLD uint32_t load_tables(WarpSmem* sm, TableIo* io, uint32_t lane) {
     t.bits = k == 0 ? (uint32_t)kCmdLutBits : k == 1 ? (uint32_t)kDistLutBits : (uint32_t)kLitLutBits;
     t.alphabet = k == 0 ? (uint32_t)bgx::kNumCmdSymbols : k == 1 ? (uint32_t)bgx::kNumDistSymbols : (uint32_t)bgx::kNumLitSymbols;
     t.sorted_u8 = k == 2 ? 1u : 0u;
-    terr = load_table(sm, rd, in, t, lane);
+    // the 512 x u16 LUT of the code-length code (sym | len << 8): behind the list in the output ring for the literal
+    // code (a list of <= 256 entries); the lists of the other two need the room -- they borrow the literal LUT, which
+    // is built last
+    uint16_t* cl_lut = k < 2u ? sm->lut_lit : reinterpret_cast<uint16_t*>(sm->ring + 1024);
+    terr = load_table(sm, rd, in, t, cl_lut, lane);
   }
   io->rd = rd;
   io->in = in;

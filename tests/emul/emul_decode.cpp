@@ -103,11 +103,15 @@ void emul_stats(uint64_t* out14, int reset) {
 uint32_t emul_table_status(const uint8_t* lens, uint32_t n) {
   bgxk::WarpSmem* sm = new bgxk::WarpSmem();
   memset(sm, 0, sizeof(*sm));
-  memcpy(sm->ring, lens, n);
+  // the compact list and the per-length counts load_table hands to build_table
+  uint16_t* list = reinterpret_cast<uint16_t*>(sm->ring);
+  uint32_t used = 0;
+  for (uint32_t s = 0; s < n; ++s)
+    if (lens[s]) { list[used++] = (uint16_t)(s | ((uint32_t)lens[s] << 10)); sm->scratch[lens[s] & 15u]++; }
   uint32_t st[32];
   wemu::run_warp([&] {
     bgxk::TableRef t{sm->lut_cmd, &sm->aux[0], sm->sorted_cmd, (uint32_t)bgxk::kCmdLutBits, (uint32_t)n, 0u};
-    st[wemu::lane()] = bgxk::build_table(sm, sm->ring, t, (uint32_t)wemu::lane());
+    st[wemu::lane()] = bgxk::build_table(sm, list, used, t, (uint32_t)wemu::lane());
   });
   uint32_t r = st[0];
   for (int l = 1; l < 32; ++l)
