@@ -419,6 +419,8 @@ BGX_DEV uint32_t huff_decode(const uint16_t* lut, const HuffAux& aux, const Sort
 // Table construction. It runs once per table and page, so it is written for SIZE: one out-of-line routine serves the
 // three tables (LUT width, alphabet and the element size of `sorted` are run-time values), which keeps a page's table phase
 // inside the instruction cache next to the round loops of the other pages on the SM.
+// scratch[] words during the table phase
+constexpr uint32_t kScrCntA = 0, kScrNext = 16, kScrClLen = 48, kScrDesc = 72;   // desc: 3 x 8 words
 struct TableRef {
   uint16_t* lut;
   HuffAux* aux;
@@ -437,7 +439,7 @@ BGX_DEV void lut_fill_coop(uint16_t* lut, uint32_t bits, uint32_t rev, uint32_t 
 
 // Builds LUT + canonical arrays of one prefix code from
 //   list[0..used)  (symbol | length << 10) of every symbol with a non-zero length, in symbol order (shared memory)
-//   sm->scratch[0..15]  the number of symbols per length
+//   cnt[1..15]      the number of symbols per length
 // Canonical order = (length, symbol index), as GenerateHuffmanTable (BrotligHuffmanTable.cpp:44-71). Work is
 // proportional to the symbols in use and to the LUT size, not to the alphabet (most of the 728 / 544 symbols of a
 // page are unused):
@@ -447,12 +449,11 @@ BGX_DEV void lut_fill_coop(uint16_t* lut, uint32_t bits, uint32_t rev, uint32_t 
 //      code space in `sorted` order, so the entries of length L are the contiguous positions [lo_L, hi_L) and entry m
 //      of that range belongs to sorted[off_L + ((m - lo_L) >> (bits - L))]; lanes take consecutive positions (the
 //      LUT index is the bit-reversed position, the stream being read least-significant bit first).
-BGX_DEV uint32_t build_table(WarpSmem* sm, const uint16_t* list, uint32_t used, const TableRef& t, uint32_t lane) {
+BGX_DEV uint32_t build_table(WarpSmem* sm, const uint16_t* list, const uint32_t* cnt, uint32_t used, const TableRef& t, uint32_t lane) {
   const uint32_t bits = t.bits;
   uint16_t* const lut = t.lut;
   HuffAux& aux = *t.aux;
-  const uint32_t* cnt = sm->scratch;  // [16]
-  uint32_t* next = sm->scratch + 16;  // [16] running position in `sorted` per length
+  uint32_t* next = sm->scratch + kScrNext;  // [16] running position in `sorted` per length
   // ---- 1. lane L (1..15) owns length L. With the counts left-aligned to 15 bits, the first code of a length is the
   //      EXCLUSIVE prefix sum over the shorter lengths (code[L] = (code[L-1] + cnt[L-1]) << 1, left-aligned), its limit
   //      the inclusive one, and the total the Kraft sum.
@@ -508,15 +509,26 @@ BGX_DEV uint32_t build_table(WarpSmem* sm, const uint16_t* list, uint32_t used, 
   // positions past the last code of <= bits bits start longer codes (a lone symbol: positions no valid stream reaches)
 #pragma unroll 1
   for (uint32_t m = __shfl_sync(kFull, hi_mine, (int)bits) + lane; m < (1u << bits); m += 32) lut[__brev(m) >> (32u - bits)] = kLongCode;
-  __syncwarp();   // (the next table's description reuses the scratch and the list)
+  __syncwarp();
   return 0u;
 }
 
-// Reads one prefix-code description (trivial / simple / complex) and builds its tables.
+// A prefix code travels from its description in the bit stream (read_table: everything that consumes bits) to LUT +
+// canonical arrays (build_from_desc) as a TableDesc and, for a complex code, the list of its used symbols + the counts
+// per length.
+struct TableDesc {
+  uint32_t type;           // 0 trivial, 1 simple, 2 complex
+  uint32_t n;              // simple: symbols (2..4); complex: entries of the list
+  uint32_t shape;          // simple: 0..3 = length shapes {1,1} {1,2,2} {2,2,2,2} {1,2,3,3}
+  uint32_t sym[4];         // trivial / simple: the symbols in stored order
+  uint32_t pad;
+};
+static_assert(sizeof(TableDesc) == 32 && kScrDesc + 24 <= 224, "table descriptors fit the scratch words");
+
+// Reads one prefix-code description (trivial / simple / complex) into `d` (+ list / cnt).
 // Returns 0 or kPageErrTable. Cursor conventions: every table starts at sub-stream 0 (lane 0).
-BGX_DEV uint32_t load_table(WarpSmem* sm, BitRd& rd, PageIn& in, const TableRef& t, uint16_t* cl_lut, uint32_t lane) {
-  const uint32_t alphabet = t.alphabet, bits = t.bits;
-  uint16_t* const lut = t.lut;
+BGX_DEV uint32_t read_table(WarpSmem* sm, BitRd& rd, PageIn& in, uint32_t alphabet, TableDesc* d, uint16_t* cl_lut, uint16_t* list,
+                            uint32_t* cnt, uint32_t lane) {
   const uint32_t max_bits = bgx::bit_length(alphabet - 1);
   br_topup(rd, in);
   uint32_t hdr = 0;
@@ -531,25 +543,12 @@ BGX_DEV uint32_t load_table(WarpSmem* sm, BitRd& rd, PageIn& in, const TableRef&
     if (type && nsym < 2) return kPageErrTable;
     uint32_t sym = 0;
     if (lane < nsym) sym = br_read(rd, in, max_bits);
-    if (!type) {
-      sym = __shfl_sync(kFull, sym, 0);
-#pragma unroll 1
-      for (uint32_t j = lane; j < (1u << bits); j += 32) lut[j] = (uint16_t)sym;   // length field 0
-      __syncwarp();
-      return 0;
+    if (lane < 4) d->sym[lane] = sym;
+    if (lane == 0) {
+      d->type = type;
+      d->n = nsym;
+      d->shape = nsym < 4 ? nsym - 2 : (tree_select ? 3u : 2u);
     }
-    // shapes {1,1} {1,2,2} {2,2,2,2} {1,2,3,3}; codes are consecutive in stored order
-    const uint32_t shape = nsym < 4 ? nsym - 2 : (tree_select ? 3u : 2u);
-    const uint32_t lens4 = shape == 0 ? 0x0011u : shape == 1 ? 0x0221u : shape == 2 ? 0x2222u : 0x3321u;
-    const uint32_t codes4 = shape == 0 ? 0x0010u : shape == 1 ? 0x0320u : shape == 2 ? 0x3210u : 0x7620u;
-#pragma unroll 1
-    for (uint32_t k = 0; k < nsym; ++k) {
-      const uint32_t sk = __shfl_sync(kFull, sym, k);
-      const uint32_t Lk = (lens4 >> (4 * k)) & 15u;
-      const uint32_t ck = (codes4 >> (4 * k)) & 15u;
-      lut_fill_coop(lut, bits, __brev(ck) >> (32 - Lk), Lk, (uint16_t)((sk & 0x3ffu) | (Lk << 10)), lane);
-    }
-    __syncwarp();
     return 0;
   }
   if (type != 2) return kPageErrTable;
@@ -559,8 +558,7 @@ BGX_DEV uint32_t load_table(WarpSmem* sm, BitRd& rd, PageIn& in, const TableRef&
   const uint32_t ncl = ((hdr >> 2) & 15u) + 4u;
   const uint32_t my_sym = lane < 4u ? lane + 1u : lane == 4u ? 0u : lane == 5u ? 5u : lane == 6u ? 17u : lane == 7u ? 6u :
                           lane == 8u ? 16u : lane - 2u;
-  uint32_t* cnt = sm->scratch;                  // [16] symbols per length of the code being described (build_table)
-  uint32_t* cl_len_by_sym = sm->scratch + 16;   // [18] (next[] is not live yet)
+  uint32_t* cl_len_by_sym = sm->scratch + kScrClLen;   // [18]
   uint32_t myread = 0;
   if (lane < 18) cl_len_by_sym[lane] = 0;   // the reference leaves these uninitialised when ncl < 18
   if (lane < 16) cnt[lane] = 0;
@@ -576,39 +574,41 @@ BGX_DEV uint32_t load_table(WarpSmem* sm, BitRd& rd, PageIn& in, const TableRef&
   const uint32_t cl_kraft = __reduce_add_sync(kFull, myread ? (512u >> myread) : 0u);
   if (cl_kraft != 512u && __popc(cl_used) != 1) return kPageErrTable;
   __syncwarp();
-  // canonical codes over symbols 0..ncl-1 (GenerateHuffmanTable is called with size = ncl, :145), but the per-length
-  // counts come from every length that was read (:135-142): the code of symbol i, left-aligned to 9 bits, is the sum
-  // of 512 >> length over the lengths read for ANY symbol that are shorter, plus those of equal length among the
-  // symbols 0..ncl-1 below i.
-  const uint32_t ls = (lane < ncl && lane < 18) ? cl_len_by_sym[lane] : 0u;   // symbol `lane` of the canonical set
-  const uint32_t lr = lane < 18 ? cl_len_by_sym[lane] : 0u;                   // every length that was read
-  uint32_t code_la = 0;
+  // canonical codes over symbols 0..ncl-1 (GenerateHuffmanTable is called with size = ncl, :145),
+  // but the per-length counts come from every length that was read (:135-142)
+  const uint32_t ls = (lane < ncl && lane < 18) ? cl_len_by_sym[lane] : 0u;
+  const uint32_t msame = __match_any_sync(kFull, ls);
+  const uint32_t rank = __popc(msame & ((1u << lane) - 1u));
+  uint32_t code = 0, mycode = 0, prevcnt = 0;
 #pragma unroll 1
-  for (uint32_t k = 0; k < 18; ++k) {
-    const uint32_t Lr = __shfl_sync(kFull, lr, (int)k), Lc = __shfl_sync(kFull, ls, (int)k);
-    if (Lr && Lr < ls) code_la += 512u >> Lr;
-    if (Lc && Lc == ls && k < lane) code_la += 512u >> Lc;
+  for (uint32_t L = 1; L <= 9; ++L) {
+    code = (code + prevcnt) << 1;
+    prevcnt = __popc(__ballot_sync(kFull, myread == L));
+    if (ls == L) mycode = code + rank;
   }
-#pragma unroll 1
-  for (uint32_t j = lane; j < 256; j += 32) reinterpret_cast<uint32_t*>(cl_lut)[j] = 0;   // sym 0, len 0 where no code lands
+  // LUT: zero (sym 0, len 0) wherever no code lands; codes owning >= 32 entries are filled by the whole warp, one code
+  // at a time, the others by their own lane (<= 16 entries each, all of them at once)
+  reinterpret_cast<uint4*>(cl_lut)[lane] = make_uint4(0u, 0u, 0u, 0u);
+  reinterpret_cast<uint4*>(cl_lut)[32u + lane] = make_uint4(0u, 0u, 0u, 0u);
   __syncwarp();
-  // LUT by position, as in build_table: symbol k owns the 512 >> L positions from its left-aligned code on
+  const uint32_t rev = ls ? (__brev(mycode) >> (32u - ls)) & 511u : 0u;
+  const uint16_t entry = (uint16_t)(lane | (ls << 8));
+  uint32_t wide = __ballot_sync(kFull, ls != 0u && ls <= 4u);
+  while (wide) {
+    const int k = __ffs((int)wide) - 1;
+    wide &= wide - 1;
+    const uint32_t Lk = __shfl_sync(kFull, ls, k);
+    lut_fill_coop(cl_lut, 9u, __shfl_sync(kFull, rev, k), Lk, (uint16_t)((uint32_t)k | (Lk << 8)), lane);
+  }
+  if (ls > 4u) {
 #pragma unroll 1
-  for (uint32_t k = 0; k < 18; ++k) {
-    const uint32_t Lk = __shfl_sync(kFull, ls, (int)k);
-    const uint32_t lo = __shfl_sync(kFull, code_la, (int)k);
-    if (!Lk) continue;
-    const uint32_t hi = lo + (512u >> Lk);
-    const uint16_t entry = (uint16_t)(k | (Lk << 8));
-#pragma unroll 1
-    for (uint32_t m = lo + lane; m < hi && m < 512u; m += 32) cl_lut[__brev(m) >> 23] = entry;
+    for (uint32_t j = rev; j < 512u; j += 1u << ls) cl_lut[j] = entry;
   }
   __syncwarp();
 
   // ---- 2) the code lengths themselves: k-th code-length symbol lives in sub-stream k mod 32. They are not stored as
   //      an array of 728 lengths: every symbol with a non-zero length goes to a compact list (symbol | length << 10,
   //      symbol order), and the lengths are counted on the way.
-  uint16_t* list = reinterpret_cast<uint16_t*>(sm->ring);
   uint32_t filled = 0, used = 0, prev_carry = bgx::kInitialRepeatLen;
 #pragma unroll 1
   while (filled < alphabet) {
@@ -646,19 +646,61 @@ BGX_DEV uint32_t load_table(WarpSmem* sm, BitRd& rd, PageIn& in, const TableRef&
     filled += __shfl_sync(kFull, incl, 31) & 0xffffu;
     used += __reduce_add_sync(kFull, nz);
   }
-  __syncwarp();
-  return build_table(sm, list, used, t, lane);
+  if (lane == 0) {
+    d->type = 2u;
+    d->n = used;
+  }
+  return 0u;
+}
+
+// LUT + canonical arrays of one code from its description.
+BGX_DEV uint32_t build_from_desc(WarpSmem* sm, const TableDesc* d, const TableRef& t, const uint16_t* list, const uint32_t* cnt, uint32_t lane) {
+  const uint32_t type = d->type, n = d->n, bits = t.bits;
+  uint16_t* const lut = t.lut;
+  if (type == 2u) return build_table(sm, list, cnt, n, t, lane);
+  if (type == 0u) {
+    const uint16_t sym = (uint16_t)d->sym[0];
+#pragma unroll 1
+    for (uint32_t j = lane; j < (1u << bits); j += 32) lut[j] = sym;   // length field 0
+  } else if (type == 1u) {
+    // codes are consecutive in stored order
+    const uint32_t shape = d->shape;
+    const uint32_t lens4 = shape == 0 ? 0x0011u : shape == 1 ? 0x0221u : shape == 2 ? 0x2222u : 0x3321u;
+    const uint32_t codes4 = shape == 0 ? 0x0010u : shape == 1 ? 0x0320u : shape == 2 ? 0x3210u : 0x7620u;
+#pragma unroll 1
+    for (uint32_t k = 0; k < n && k < 4u; ++k) {
+      const uint32_t Lk = (lens4 >> (4 * k)) & 15u;
+      const uint32_t ck = (codes4 >> (4 * k)) & 15u;
+      lut_fill_coop(lut, bits, __brev(ck) >> (32 - Lk), Lk, (uint16_t)((d->sym[k] & 0x3ffu) | (Lk << 10)), lane);
+    }
+  }
+  return 0u;
 }
 
 // The three prefix codes of a page -- insert&copy (728 symbols), distance (544), literal (256), in stream order
 // (PageDecoder.cpp:126-147) -- read and built by ONE out-of-line routine working on copies of the reader state.
+// Where a description lives between read_table and build_from_desc:
+//   code 0: list in the output ring [0, 1456);   code-length-code LUT (512 x u16) in litq + lut_lit[0, 256)
+//   code 1: list in lut_lit[256, 1024) (1536 B >= 1088);   the same code-length-code LUT
+//   code 2: list in the output ring [0, 512);   code-length-code LUT in the output ring [1024, 2048)
+// (the literal LUT is built last, from the ring, when everything that borrowed its room is dead).
+// Measured and dropped: the consumer warp building table k while the producer reads description k + 1 (two CTA
+// barriers per table): +-0 on 4 KiB pages, whose table phase is bound by instruction FETCH -- the code of a phase
+// that runs once per page is cold every time -- not by the instructions it executes; 16 KiB pages lost 3.6 %.
 struct TableIo { BitRd rd; PageIn in; };
+BGX_DEV TableDesc* table_desc(WarpSmem* sm, uint32_t k) { return reinterpret_cast<TableDesc*>(sm->scratch + kScrDesc) + k; }
+BGX_DEV uint16_t* table_list(WarpSmem* sm, uint32_t k) { return k == 1u ? sm->lut_lit + 256 : reinterpret_cast<uint16_t*>(sm->ring); }
+static_assert(offsetof(WarpSmem, lut_lit) == offsetof(WarpSmem, litq) + kLitQ && kLitQ == 512 && (1 << kLitLutBits) >= 256 + bgx::kNumDistSymbols,
+              "table phase: litq + the head of lut_lit hold a code-length-code LUT, the rest of lut_lit the distance list");
+
 BGX_COLD uint32_t load_tables(WarpSmem* sm, TableIo* io, uint32_t lane) {
   BitRd rd = io->rd;
   PageIn in = io->in;
   uint32_t terr = 0;
 #pragma unroll 1
   for (uint32_t k = 0; k < 3u && !terr; ++k) {
+    TableDesc* d = table_desc(sm, k);
+    uint32_t* cnt = sm->scratch + kScrCntA;
     TableRef t;
     t.lut = k == 0 ? sm->lut_cmd : k == 1 ? sm->lut_dist : sm->lut_lit;
     t.aux = &sm->aux[k];
@@ -666,17 +708,16 @@ BGX_COLD uint32_t load_tables(WarpSmem* sm, TableIo* io, uint32_t lane) {
     t.bits = k == 0 ? (uint32_t)kCmdLutBits : k == 1 ? (uint32_t)kDistLutBits : (uint32_t)kLitLutBits;
     t.alphabet = k == 0 ? (uint32_t)bgx::kNumCmdSymbols : k == 1 ? (uint32_t)bgx::kNumDistSymbols : (uint32_t)bgx::kNumLitSymbols;
     t.sorted_u8 = k == 2 ? 1u : 0u;
-    // the 512 x u16 LUT of the code-length code (sym | len << 8): behind the list in the output ring for the literal
-    // code (a list of <= 256 entries); the lists of the other two need the room -- they borrow the literal LUT, which
-    // is built last
-    uint16_t* cl_lut = k < 2u ? sm->lut_lit : reinterpret_cast<uint16_t*>(sm->ring + 1024);
-    terr = load_table(sm, rd, in, t, cl_lut, lane);
+    uint16_t* cl_lut = k < 2u ? reinterpret_cast<uint16_t*>(sm->litq) : reinterpret_cast<uint16_t*>(sm->ring + 1024);
+    terr = read_table(sm, rd, in, t.alphabet, d, cl_lut, table_list(sm, k), cnt, lane);
+    __syncwarp();
+    if (!terr) terr = build_from_desc(sm, d, t, table_list(sm, k), cnt, lane);
+    __syncwarp();
   }
   io->rd = rd;
   io->in = in;
   return terr;
 }
-
 
 // ---------------------------------------------------------------------------------------------
 struct PageJob {

@@ -97,3 +97,15 @@ if os.environ.get("STALLS"):
     for role, d in st.items():
         tot = sum(d.values())
         print(role, tot, {k[6:]: round(100.0 * v / max(tot, 1), 1) for k, v in d.most_common(9)})
+
+if os.environ.get("REASON"):     # lines ranked by the samples of one stall reason, e.g. REASON=long_sb
+    col = next(h for h in hdr if h.startswith("stall_" + os.environ["REASON"]) and "Not Issued" not in h)
+    per = collections.Counter()
+    for (key, _), r in zip(lines_of, sass):
+        per[key] += int(r[hdr.index(col)] or 0)
+    tot = max(sum(per.values()), 1)
+    print(f"---- {col}: {tot} samples ({100.0 * tot / tot_s:.1f}% of all)")
+    for key, v in per.most_common(25):
+        if key:
+            f, n = key
+            print(f"{f[:4]}:{n:5d} {100.0 * v / tot:5.1f}%  {src[f][n - 1].strip()[:110] if f in src else ''}")

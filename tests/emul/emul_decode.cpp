@@ -111,7 +111,7 @@ uint32_t emul_table_status(const uint8_t* lens, uint32_t n) {
   uint32_t st[32];
   wemu::run_warp([&] {
     bgxk::TableRef t{sm->lut_cmd, &sm->aux[0], sm->sorted_cmd, (uint32_t)bgxk::kCmdLutBits, (uint32_t)n, 0u};
-    st[wemu::lane()] = bgxk::build_table(sm, list, used, t, (uint32_t)wemu::lane());
+    st[wemu::lane()] = bgxk::build_table(sm, list, sm->scratch, used, t, (uint32_t)wemu::lane());
   });
   uint32_t r = st[0];
   for (int l = 1; l < 32; ++l)
