@@ -84,9 +84,10 @@ constexpr uint32_t kLitQ = BGX_LITQ;  // literal ring bytes (power of two): the 
 constexpr uint32_t kRing = BGX_RING;      // output ring bytes (power of two, >= kFlushChunk + kRoundMax)
 constexpr uint32_t kRoundMax = 1024;  // largest round (bytes produced) the ring path accepts
 #ifndef BGX_SPLIT_LITS
-#define BGX_SPLIT_LITS 256
+#define BGX_SPLIT_LITS 384
 #endif
-constexpr uint32_t kSplitLits = BGX_SPLIT_LITS;  // literals per virtual round when a long round is split (two fit the literal ring)
+constexpr uint32_t kSplitLits = BGX_SPLIT_LITS;  // literals per virtual round when a long round is split (384 of the 512-byte literal ring:
+                                                 // fewer, larger virtual rounds beat two rounds of 256 in flight -- textures +2.5 %)
 static_assert((kLitQ & (kLitQ - 1)) == 0 && kSplitLits + 128 <= kLitQ, "a virtual round's literals (+ rows decoded ahead) must fit the literal ring");
 constexpr uint32_t kFlushChunk = 512; // 32 lanes x 16 B
 constexpr uint32_t kCoopLen = 32;     // inserts/copies at least this long are done by the whole warp
@@ -744,6 +745,9 @@ BGX_DEV void flush_bytes(const WarpSmem* sm, uint8_t* out, uint32_t from, uint32
   for (uint32_t p = from + lane; p < to; p += 32) out[p] = sm->ring[p & (kRing - 1)];
 }
 
+#ifndef BGX_LIT_TOPUP_MASK
+#define BGX_LIT_TOPUP_MASK 6   // staging top-up when (literal index & mask) == 0: 6 = every 4th pair, 0 = every pair
+#endif
 // Decodes `cnt` literals in this lane (lane-dependent count allowed) into the literal ring at
 // page-global literal indices tail + j*32 + lane.
 BGX_DEV void decode_literals(WarpSmem* sm, BitRd& rd, PageIn& in, uint32_t tail, uint32_t cnt, uint32_t lane) {
@@ -753,7 +757,10 @@ BGX_DEV void decode_literals(WarpSmem* sm, BitRd& rd, PageIn& in, uint32_t tail,
   // with a pair whose second half is neither stored nor consumed.
 #pragma unroll 1
   for (uint32_t j = 0; j < cnt; j += 2) {
-    br_topup1(rd, in);
+    // staging top-up every 4th pair: 4 pairs consume at most 120 bits = 4 words, the most one top-up covers. The lanes
+    // cross their 16-byte chunks at different pairs, so a top-up per pair runs its body (wait + address + cp.async)
+    // nearly every time for three or four lanes; every 4th pair it runs a quarter as often for half the warp.
+    if ((j & (uint32_t)BGX_LIT_TOPUP_MASK) == 0u) br_topup1(rd, in);
     const uint32_t pk = br_peek(rd);
     uint32_t len1, len2;
     const uint32_t s1 = huff_decode<kLitLutBits>(sm->lut_lit, sm->aux[2], sm->sorted_lit, bgx::kNumLitSymbols, pk, len1);
@@ -963,13 +970,22 @@ BGX_COLD bool slow_round(SlowRound* a) {
       else if (v_cpy > kRoundMax - v_ins) v_cpy = kRoundMax - v_ins;
     }
     const bool clipped = __ballot_sync(kFull, lane == a0 && (v_ins != rem_ins || v_cpy != rem_cpy)) != 0u;
-    const uint64_t vincl = warp_incl_scan64(((uint64_t)(v_ins + v_cpy) << 32) | v_ins, lane);
-    const bool ok = (uint32_t)(vincl >> 32) <= kRoundMax && (uint32_t)vincl <= kSplitLits;
-    const uint32_t notok = ~__ballot_sync(kFull, ok) & ~(0xffffffffu >> (31u - (a0 & 31u)));   // lanes > a0 that do not fit
-    const uint32_t b0 = a0 >= 32u ? 32u : clipped ? a0 + 1u : (notok ? (uint32_t)(__ffs((int)notok) - 1) : 32u);
-    if (lane >= b0) { v_ins = 0; v_cpy = 0; }
-    const uint64_t vtot = __shfl_sync(kFull, vincl, (int)((b0 ? b0 : 1u) - 1u));   // sums over the taken commands
-    const uint64_t vpk = lane < b0 ? vincl : vtot;
+    uint64_t vtot, vpk;
+    if (clipped) {
+      // a piece of the leading command is the whole virtual round (the usual case inside a long literal run: every
+      // virtual round but the last of a command): its sums are the piece itself from lane a0 on -- no scan
+      vtot = __shfl_sync(kFull, ((uint64_t)(v_ins + v_cpy) << 32) | v_ins, (int)a0);
+      vpk = lane < a0 ? 0ull : vtot;
+      if (lane != a0) { v_ins = 0; v_cpy = 0; }
+    } else {
+      const uint64_t vincl = warp_incl_scan64(((uint64_t)(v_ins + v_cpy) << 32) | v_ins, lane);
+      const bool ok = (uint32_t)(vincl >> 32) <= kRoundMax && (uint32_t)vincl <= kSplitLits;
+      const uint32_t notok = ~__ballot_sync(kFull, ok) & ~(0xffffffffu >> (31u - (a0 & 31u)));   // lanes > a0 that do not fit
+      const uint32_t b0 = a0 >= 32u ? 32u : (notok ? (uint32_t)(__ffs((int)notok) - 1) : 32u);
+      if (lane >= b0) { v_ins = 0; v_cpy = 0; }
+      vtot = __shfl_sync(kFull, vincl, (int)((b0 ? b0 : 1u) - 1u));   // sums over the taken commands
+      vpk = lane < b0 ? vincl : vtot;
+    }
     const uint32_t vr_ins = (uint32_t)vtot;
     rem_ins -= v_ins;
     rem_cpy -= v_cpy;
