@@ -690,9 +690,10 @@ BGX_DEV uint32_t build_from_desc(WarpSmem* sm, const TableDesc* d, const TableRe
 // that runs once per page is cold every time -- not by the instructions it executes; 16 KiB pages lost 3.6 %.
 struct TableIo { BitRd rd; PageIn in; };
 BGX_DEV TableDesc* table_desc(WarpSmem* sm, uint32_t k) { return reinterpret_cast<TableDesc*>(sm->scratch + kScrDesc) + k; }
-BGX_DEV uint16_t* table_list(WarpSmem* sm, uint32_t k) { return k == 1u ? sm->lut_lit + 256 : reinterpret_cast<uint16_t*>(sm->ring); }
-static_assert(offsetof(WarpSmem, lut_lit) == offsetof(WarpSmem, litq) + kLitQ && kLitQ == 512 && (1 << kLitLutBits) >= 256 + bgx::kNumDistSymbols,
-              "table phase: litq + the head of lut_lit hold a code-length-code LUT, the rest of lut_lit the distance list");
+constexpr uint32_t kClLutSpill = kLitQ >= 1024u ? 0u : (1024u - kLitQ) / 2u;   // u16 entries of lut_lit under the code-length-code LUT
+BGX_DEV uint16_t* table_list(WarpSmem* sm, uint32_t k) { return k == 1u ? sm->lut_lit + kClLutSpill : reinterpret_cast<uint16_t*>(sm->ring); }
+static_assert(offsetof(WarpSmem, lut_lit) == offsetof(WarpSmem, litq) + kLitQ && kLitQ >= 512 && (1 << kLitLutBits) >= kClLutSpill + bgx::kNumDistSymbols,
+              "table phase: litq (+ the head of lut_lit) hold a code-length-code LUT, the rest of lut_lit the distance list");
 
 BGX_COLD uint32_t load_tables(WarpSmem* sm, TableIo* io, uint32_t lane) {
   BitRd rd = io->rd;
