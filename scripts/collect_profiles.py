@@ -66,6 +66,18 @@ traffic["_comment"] = ("dram__bytes_read.sum + dram__bytes_write.sum of the deco
                        "(scripts/gpu_evidence.sh; details pages: profiles/<tag>_prof_*_details.csv), as a ratio to the algorithmic bytes of the "
                        "captured launch (compressed bytes read + decompressed bytes written); bench.py multiplies the ratio by the algorithmic "
                        "bytes of its own launch.")
+# the 4 KiB-page capture: details page + instructions / stall samples per code region (scripts/ncu_regions.py;
+# needs the library the capture was taken with: build/variants/libbgx_<tag>final.so, else the in-tree build)
+rep4k = SRC + "page4k.ncu-rep"
+if os.path.exists(rep4k):
+    det = subprocess.run(["ncu", "-i", rep4k, "--page", "details", "--csv"], capture_output=True, text=True).stdout
+    open(os.path.join(DST, f"{tag}_prof_page4k_details.csv"), "w").write(det)
+    lib = os.path.join(ROOT, "build", "variants", f"libbgx_{tag}final.so")
+    if not os.path.exists(lib):
+        lib = os.path.join(ROOT, "brotli_g_sdk_b200", "libbrotlig_b200.so")
+    reg = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "ncu_regions.py"), rep4k, lib, "196608"], capture_output=True, text=True).stdout
+    open(os.path.join(DST, f"{tag}_prof_page4k_regions.txt"), "w").write(
+        "# 4 KiB single-page streams, 1 GiB mixed: warp instructions per COMPRESSED page (196 608 of the 262 144 pages) and stall samples per code region\n" + reg)
 ALGO = {}   # algorithmic bytes of the captured launches, from the logs of gpu_prof_one.py
 for kind, log in (("mixed", "ncu_mixed.log"), ("random", "ncu_raw.log"), ("texture", "ncu_texture.log")):
     rep = SRC + {"mixed": "mixed", "random": "raw", "texture": "texture"}[kind] + ".ncu-rep"
