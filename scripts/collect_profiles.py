@@ -36,12 +36,12 @@ def last_json_line(path):
 
 
 # ---- bench lines (one JSON object per file, pretty enough to diff)
-for name in ("bench_n1.json", "bench_reference_arm.json", "bench_random.json", "bench_texture.json"):
+for name in ("bench_n1.json", "bench_reference_arm.json", "bench_random.json", "bench_texture.json", "bench_n2.json", "bench_n8.json"):   # (n2 / n8: separate multi-GPU calls)
     if have(name):
         obj = last_json_line(SRC + name)
         if obj:
             json.dump(obj, open(os.path.join(DST, f"{tag}_{name}"), "w"), indent=1)
-for name in ("pytest.log", "config0.log", "kinds.log", "launches.csv", "page_size_sweep.json", "sweep_dram.csv",
+for name in ("pytest.log", "pytest_multi.log", "config0.log", "kinds.log", "launches.csv", "page_size_sweep.json", "sweep_dram.csv",
              "sanitizer_memcheck.log", "sanitizer_synccheck.log", "sanitizer_racecheck_lockstep.log", "sanitizer_racecheck_production.log"):
     copy(name)
 
