@@ -162,6 +162,7 @@ BGX_DEV saddr_t saddr(const void* p) { return reinterpret_cast<uintptr_t>(p); }
 BGX_DEV saddr_t saddr_pinned(const void* p) { return reinterpret_cast<uintptr_t>(p); }
 BGX_DEV uint32_t lds_u8(saddr_t a) { return *reinterpret_cast<const uint8_t*>(a); }
 BGX_DEV void sts_u8(saddr_t a, uint32_t v) { *reinterpret_cast<uint8_t*>(a) = (uint8_t)v; }
+BGX_DEV uint32_t lds_u16(saddr_t a) { return *reinterpret_cast<const uint16_t*>(a); }
 BGX_DEV uint32_t lds_u32(saddr_t a) { return *reinterpret_cast<const uint32_t*>(a); }
 BGX_DEV uint2 lds_u32x2(saddr_t a) { return *reinterpret_cast<const uint2*>(a); }
 BGX_DEV void sts_u32(saddr_t a, uint32_t v) { *reinterpret_cast<uint32_t*>(a) = v; }
@@ -178,6 +179,7 @@ BGX_DEV saddr_t saddr(const void* p) { return (uint32_t)__cvta_generic_to_shared
 BGX_DEV saddr_t saddr_pinned(const void* p) { uint32_t a = (uint32_t)__cvta_generic_to_shared(p); asm volatile("" : "+r"(a)); return a; }
 BGX_DEV uint32_t lds_u8(saddr_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 BGX_DEV void sts_u8(saddr_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+BGX_DEV uint32_t lds_u16(saddr_t a) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 BGX_DEV uint32_t lds_u32(saddr_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 BGX_DEV uint2 lds_u32x2(saddr_t a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
 BGX_DEV void sts_u32(saddr_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
@@ -189,6 +191,16 @@ BGX_DEV uint32_t ldg_u32(const uint32_t* p) { uint32_t v; asm volatile("ld.globa
 #endif
 
 // keeps a loop-invariant value in its register (the optimiser otherwise re-derives cheap ones inside hot loops)
+// base + 2 * index as ONE multiply-add (the compiler otherwise doubles, masks and adds)
+BGX_DEV saddr_t saddr_scaled2(saddr_t base, uint32_t index) {
+#ifdef BGX_EMULATED
+  return base + 2u * index;
+#else
+  uint32_t a;
+  asm("mad.lo.u32 %0, %1, 2, %2;" : "=r"(a) : "r"(index), "r"(base));
+  return a;
+#endif
+}
 BGX_DEV uint32_t pinned(uint32_t v) {
 #ifndef BGX_EMULATED
   asm volatile("" : "+r"(v));
@@ -398,14 +410,9 @@ BGX_DEV uint64_t warp_incl_scan64(uint64_t v, uint32_t lane) {   // two 32-bit s
 
 // ---------------------------------------------------------------------------------------------
 // prefix-code decode: primary LUT entry = symbol | length << 10; kLongCode => canonical search.
+// The canonical search behind a kLongCode entry (codes longer than the LUT index).
 template <int BITS, typename SortedT>
-BGX_DEV uint32_t huff_decode(const uint16_t* lut, const HuffAux& aux, const SortedT* sorted, uint32_t nsym,
-                             uint32_t peek, uint32_t& len) {
-  const uint32_t e = lut[peek & ((1u << BITS) - 1u)];
-  if (e != kLongCode) {
-    len = e >> 10;
-    return e & 0x3ffu;
-  }
+BGX_DEV uint32_t huff_decode_long(const HuffAux& aux, const SortedT* sorted, uint32_t nsym, uint32_t peek, uint32_t& len) {
   const uint32_t msb = __brev(peek) >> 17;   // first 15 stream bits as an MSB-first number
   uint32_t L = BITS + 1;
 #pragma unroll 1
@@ -414,6 +421,28 @@ BGX_DEV uint32_t huff_decode(const uint16_t* lut, const HuffAux& aux, const Sort
   uint32_t idx = (uint16_t)(aux.base[L] + (msb >> (15u - L)));
   if (idx >= nsym) idx = nsym - 1;
   return sorted[idx];
+}
+template <int BITS, typename SortedT>
+BGX_DEV uint32_t huff_decode(const uint16_t* lut, const HuffAux& aux, const SortedT* sorted, uint32_t nsym,
+                             uint32_t peek, uint32_t& len) {
+  const uint32_t e = lut[peek & ((1u << BITS) - 1u)];
+  if (e != kLongCode) {
+    len = e >> 10;
+    return e & 0x3ffu;
+  }
+  return huff_decode_long<BITS, SortedT>(aux, sorted, nsym, peek, len);
+}
+// The same with the LUT given as a shared-window address held in a register (the literal loop: through the generic
+// pointer the compiler re-derives the window base -- S2UR + ULEA -- in every trip).
+template <int BITS, typename SortedT>
+BGX_DEV uint32_t huff_decode_at(saddr_t lut_a, const HuffAux& aux, const SortedT* sorted, uint32_t nsym,
+                                uint32_t peek, uint32_t& len) {
+  const uint32_t e = lds_u16(saddr_scaled2(lut_a, peek & ((1u << BITS) - 1u)));
+  if (e != kLongCode) {
+    len = e >> 10;
+    return e & 0x3ffu;
+  }
+  return huff_decode_long<BITS, SortedT>(aux, sorted, nsym, peek, len);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -752,7 +781,7 @@ BGX_DEV void flush_bytes(const WarpSmem* sm, uint8_t* out, uint32_t from, uint32
 // Decodes `cnt` literals in this lane (lane-dependent count allowed) into the literal ring at
 // page-global literal indices tail + j*32 + lane.
 BGX_DEV void decode_literals(WarpSmem* sm, BitRd& rd, PageIn& in, uint32_t tail, uint32_t cnt, uint32_t lane) {
-  const saddr_t litq_a = saddr(sm->litq);
+  const saddr_t litq_a = saddr_pinned(sm->litq), lut_a = saddr_pinned(sm->lut_lit);
   uint32_t q = (tail + lane) & (kLitQ - 1);
   // two literals per 32-bit peek (2 x 15 bits at most): one window refill check per pair. An odd count ends
   // with a pair whose second half is neither stored nor consumed.
@@ -764,8 +793,8 @@ BGX_DEV void decode_literals(WarpSmem* sm, BitRd& rd, PageIn& in, uint32_t tail,
     if ((j & (uint32_t)BGX_LIT_TOPUP_MASK) == 0u) br_topup1(rd, in);
     const uint32_t pk = br_peek(rd);
     uint32_t len1, len2;
-    const uint32_t s1 = huff_decode<kLitLutBits>(sm->lut_lit, sm->aux[2], sm->sorted_lit, bgx::kNumLitSymbols, pk, len1);
-    const uint32_t s2 = huff_decode<kLitLutBits>(sm->lut_lit, sm->aux[2], sm->sorted_lit, bgx::kNumLitSymbols, pk >> len1, len2);
+    const uint32_t s1 = huff_decode_at<kLitLutBits>(lut_a, sm->aux[2], sm->sorted_lit, bgx::kNumLitSymbols, pk, len1);
+    const uint32_t s2 = huff_decode_at<kLitLutBits>(lut_a, sm->aux[2], sm->sorted_lit, bgx::kNumLitSymbols, pk >> len1, len2);
     const bool two = j + 1u < cnt;
     sts_u8(litq_a + q, s1);
     if (two) sts_u8(litq_a + ((q + 32u) & (kLitQ - 1)), s2);
@@ -1091,6 +1120,7 @@ BGX_DEV void producer_warp(const PageJob& job, WarpSmem* sm) {
     return;
   }
   const uint32_t postfix_mask = (1u << npostfix) - 1u;
+  const saddr_t smem_a = saddr_pinned(sm);   // the page arena as a shared-window address (LUT look-ups: one multiply-add + LDS)
   for (;;) {
     if (!pc.acquire_slot()) break;
     br_topup1(rd, in);
@@ -1099,7 +1129,7 @@ BGX_DEV void producer_warp(const PageJob& job, WarpSmem* sm) {
     //      fields branch off.
     const uint32_t pk = br_peek(rd);
     uint32_t len;
-    const uint32_t sym = huff_decode<kCmdLutBits>(sm->lut_cmd, sm->aux[0], sm->sorted_cmd, bgx::kNumCmdSymbols, pk, len);
+    const uint32_t sym = huff_decode_at<kCmdLutBits>(smem_a + (uint32_t)offsetof(WarpSmem, lut_cmd), sm->aux[0], sm->sorted_cmd, bgx::kNumCmdSymbols, pk, len);
     const uint32_t sent = __ballot_sync(kFull, sym == (uint32_t)bgx::kCmdSentinel);
     const uint32_t n = umin32((uint32_t)__ffs((int)sent) - 1u, 32u);       // commands in this round (no sentinel: ffs = 0)
     pdone = sent != 0;
@@ -1107,8 +1137,9 @@ BGX_DEV void producer_warp(const PageJob& job, WarpSmem* sm) {
     const bool has_copy = sym < (uint32_t)bgx::kCmdSentinel;            // else insert-only (PageDecoder.cpp:308-317)
     uint32_t ic = sym - (uint32_t)bgx::kCmdSentinel;
     ic = has_copy ? bgx::icp_insert_code(sym) : (ic > 23u ? 23u : ic);
-    const uint32_t ei = sm->lenlut[ic];
-    const uint32_t ec = has_copy ? sm->lenlut[24u + bgx::icp_copy_code(sym)] : 0u;
+    const saddr_t lenlut_a = smem_a + (uint32_t)offsetof(WarpSmem, lenlut);
+    const uint32_t ei = lds_u32(lenlut_a + 4u * ic);
+    const uint32_t ec = has_copy ? lds_u32(lenlut_a + 96u + 4u * bgx::icp_copy_code(sym)) : 0u;
     const uint32_t nbi = ei >> 16, nbc = ec >> 16;
     uint32_t adv = len + nbi + nbc;
     uint32_t ins = ei & 0xffffu, cpy = ec & 0xffffu;
@@ -1137,7 +1168,7 @@ BGX_DEV void producer_warp(const PageJob& job, WarpSmem* sm) {
         if (sym >= 128u) {
           const uint32_t pk2 = br_peek(rd);
           uint32_t len2;
-          const uint32_t dcode = huff_decode<kDistLutBits>(sm->lut_dist, sm->aux[1], sm->sorted_dist, bgx::kNumDistSymbols, pk2, len2);
+          const uint32_t dcode = huff_decode_at<kDistLutBits>(smem_a + (uint32_t)offsetof(WarpSmem, lut_dist), sm->aux[1], sm->sorted_dist, bgx::kNumDistSymbols, pk2, len2);
           const bool expl = dcode >= 16u + ndirect;                     // distance with extra bits (PageDecoder.cpp:376-394)
           const uint32_t v = dcode - ndirect - 16u;
           uint32_t nb = 1u + (v >> (npostfix + 1u));
@@ -1517,7 +1548,7 @@ BGX_DEV void consumer_warp(const PageJob& job, WarpSmem* sm) {
       }
       while (pos - flushed >= kFlushChunk) {
         const uint32_t f = flushed + 16u * lane;
-        *reinterpret_cast<uint4*>(outb + f) = *reinterpret_cast<const uint4*>(&sm->ring[f & (kRing - 1)]);
+        *reinterpret_cast<uint4*>(outb + f) = lds_u32x4(ring_at(ring_a, f));
         flushed += kFlushChunk;
       }
       __syncwarp();

@@ -219,6 +219,24 @@ def test_page_size_sweep_small_single_page_streams(sdk, oracle, dec):
     assert np.array_equal(oracle.decode(streams[7]), sources[7])
 
 
+def test_thousands_of_ragged_streams_in_one_launch(sdk, dec):
+    """More streams than resident CTAs, with uneven page counts: every CTA walks the flat page queue across many
+    streams, so the kernel's stream look-up runs its proportional guess, its neighbour check and its fallback search."""
+    from brotli_g_sdk_b200 import datagen
+    rng = np.random.default_rng(77)
+    uniq = []
+    for i, n in enumerate([1, 300, 1500, 4096, 9000, 16384, 40000, 65536, 65537, 150000, 200000, 333]):
+        d = datagen.mixed(n, seed=300 + i) if n > 2000 else datagen.text_like(n, seed=300 + i)
+        uniq.append((d, sdk.Encode(d)))
+    # long stretches of one-page streams with a few many-page streams in between, then a ragged tail
+    order = [0, 1, 2, 3] * 900 + [9, 10] * 8 + [4, 5] * 700 + list(rng.integers(0, len(uniq), size=1500))
+    streams = [uniq[k][1] for k in order]
+    outs, ms = dec.decode_batch_host(streams)
+    assert ms > 0 and len(outs) == len(order)
+    for j, k in enumerate(order):
+        assert np.array_equal(outs[j], uniq[k][0]), f"stream {j} (kind {k}) != source bytes"
+
+
 def test_plan_rejects_bad_buffers(sdk, dec):
     """device-resident contract: 16-byte aligned stream pointer, capacity covering the stream rounded up to 16"""
     import torch
