@@ -865,24 +865,19 @@ BGX_DEV bool mbar_wait(saddr_t a, uint32_t parity) {
   wemu::mbar_wait(reinterpret_cast<uint64_t*>(a), parity);
   return true;
 #else
-  // try_wait comes back after a short, hardware-bounded time whatever limit it is given (measured: ~20 cycles per
-  // poll). Hand-overs between rounds take a few polls and must be seen at once (sleeping from the 16th poll on costs
+  // try_wait comes back after a short time whatever limit it is given. Hand-overs between rounds take a few polls and must be seen at once (sleeping from the 16th poll on costs
   // structured binary 2.5 % and 16 KiB pages 5 %); only a warp that has polled kFastPolls times (~10 us: the consumer
   // during a table phase, or a page that hangs) sleeps between polls. The poll count doubles as the hang guard
   // (kMaxPolls sleeping polls are far beyond any wait of a valid stream).
+  // (A try_wait with a time limit is three instructions -- SYNCS.PHASECHK.TRYWAIT, NANOSLEEP.SYNCS, SYNCS.PHASECHK -- and
+  // the sleep ends with ANY barrier event on the SM, so a waiting warp polls every ~90 cycles while 16 pages hand rounds
+  // over. A tighter poll loop written in PTX, four polls per trip, halved the instructions per poll and lost 1-4 %.)
   uint32_t done, polls = 0;
   for (;;) {
-#if BGX_WAIT_HINT_NS > 0
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(a), "r"(parity), "r"((uint32_t)BGX_WAIT_HINT_NS) : "memory");
-#else
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(a), "r"(parity) : "memory");
-#endif
     if (done) return true;
     if (++polls > kFastPolls) {
       if (polls > kMaxPolls) return false;
