@@ -120,6 +120,36 @@ uint32_t emul_table_status(const uint8_t* lens, uint32_t n) {
   return r;
 }
 
+// build_table on a given set of code lengths, returning what it built: the LUT (1 << bits entries), `sorted`
+// (n entries, widened to u16), limit[16] and base[16]. kind 0: the 9-bit insert&copy tables (u16 sorted), kind 2: the
+// literal tables (10-bit LUT, u8 sorted, n <= 256). Returns the status every lane agreed on.
+uint32_t emul_build_table(const uint8_t* lens, uint32_t n, uint32_t kind, uint16_t* lut_out, uint16_t* sorted_out, uint16_t* limit_out,
+                          uint16_t* base_out) {
+  bgxk::WarpSmem* sm = new bgxk::WarpSmem();
+  memset(sm, 0xa5, sizeof(*sm));     // stale bytes everywhere: whatever build_table does not write must not matter
+  memset(sm->scratch, 0, sizeof(sm->scratch));
+  uint16_t* list = reinterpret_cast<uint16_t*>(sm->ring);
+  uint32_t used = 0;
+  for (uint32_t s = 0; s < n; ++s)
+    if (lens[s]) { list[used++] = (uint16_t)(s | ((uint32_t)lens[s] << 10)); sm->scratch[lens[s] & 15u]++; }
+  uint32_t st[32];
+  const uint32_t bits = kind == 2 ? (uint32_t)bgxk::kLitLutBits : (uint32_t)bgxk::kCmdLutBits;
+  wemu::run_warp([&] {
+    bgxk::TableRef t{kind == 2 ? sm->lut_lit : sm->lut_cmd, &sm->aux[kind], kind == 2 ? (void*)sm->sorted_lit : (void*)sm->sorted_cmd, bits, n,
+                     kind == 2 ? 1u : 0u};
+    st[wemu::lane()] = bgxk::build_table(sm, list, sm->scratch, used, t, (uint32_t)wemu::lane());
+  });
+  uint32_t r = st[0];
+  for (int l = 1; l < 32; ++l)
+    if (st[l] != r) r = 0xffffffffu;
+  memcpy(lut_out, kind == 2 ? sm->lut_lit : sm->lut_cmd, sizeof(uint16_t) << bits);
+  for (uint32_t i = 0; i < n; ++i) sorted_out[i] = kind == 2 ? (uint16_t)sm->sorted_lit[i] : sm->sorted_cmd[i];
+  memcpy(limit_out, sm->aux[kind].limit, 32);
+  memcpy(base_out, sm->aux[kind].base, 32);
+  delete sm;
+  return r;
+}
+
 uint32_t emul_warp_smem_bytes() { return (uint32_t)sizeof(bgxk::WarpSmem); }
 
 // The host-pointer pipeline's segment planner (host_plan.h), for the CPU unit test. Writes 7 numbers per segment

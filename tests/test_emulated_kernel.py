@@ -101,3 +101,71 @@ def test_texture_header_with_a_lying_pitch_is_rejected(sdk, emulator):
                                          ctypes.c_uint32(512), st, fl, ctypes.byref(coll))
     assert rc == 14, rc            # BROTLIG_ERROR_CORRUPT_STREAM
     assert not out.any()
+
+
+def _random_complete_code(rng, n_used, max_len=15):
+    """code lengths of a complete prefix code with n_used symbols: split leaves of a binary tree at random"""
+    lens = [0]
+    while len(lens) < n_used:
+        cand = [i for i, l in enumerate(lens) if l < max_len]
+        if not cand:
+            break
+        i = cand[int(rng.integers(0, len(cand)))]
+        l = lens.pop(i)
+        lens += [l + 1, l + 1]
+    return lens
+
+
+def test_build_table_against_a_canonical_reference(emulator):
+    """LUT, sorted[], limit[] and base[] of build_table for random complete prefix codes of every shape (few / many
+    symbols, all lengths up to 15, gaps in the alphabet), against a plain canonical-code construction
+    (GenerateHuffmanTable, BrotligHuffmanTable.cpp:44-71: codes per length in symbol order)."""
+    import ctypes
+    rng = np.random.default_rng(2024)
+    f = emulator.lib.emul_build_table
+    f.restype = ctypes.c_uint32
+    cases = []
+    for kind, alphabet, bits in ((0, 728, 9), (2, 256, 10)):
+        for n_used in (2, 3, 5, 17, 64, 200, alphabet):
+            for rep in range(3):
+                cases.append((kind, alphabet, bits, _random_complete_code(rng, n_used)))
+        cases.append((kind, alphabet, bits, [8] * 256))                  # flat
+        cases.append((kind, alphabet, bits, [1] + list(range(2, 16)) + [15]))   # one code of every length
+        cases.append((kind, alphabet, bits, [15] * 2 + list(range(14, 0, -1))))
+    for kind, alphabet, bits, code in cases:
+        lens = np.zeros(alphabet, np.uint8)
+        where = np.sort(rng.choice(alphabet, size=len(code), replace=False))
+        lens[where] = rng.permutation(code)
+        lut = np.zeros(1 << bits, np.uint16)
+        srt = np.zeros(alphabet, np.uint16)
+        limit = np.zeros(16, np.uint16)
+        base = np.zeros(16, np.uint16)
+        st = f(ctypes.c_void_p(lens.ctypes.data), alphabet, kind, ctypes.c_void_p(lut.ctypes.data), ctypes.c_void_p(srt.ctypes.data),
+               ctypes.c_void_p(limit.ctypes.data), ctypes.c_void_p(base.ctypes.data))
+        assert st == 0, (kind, code)
+        # reference construction
+        order = sorted((int(l), int(s)) for s, l in enumerate(lens) if l)
+        cnt = [0] * 16
+        for l, _ in order:
+            cnt[l] += 1
+        first, off, c, o = [0] * 16, [0] * 16, 0, 0
+        for L in range(1, 16):
+            c = (c + cnt[L - 1]) << 1
+            first[L], off[L] = c, o
+            o += cnt[L]
+        assert [s for _, s in order] == list(srt[: len(order)]), "sorted[]"
+        for L in range(1, 16):
+            assert int(limit[L]) == min(0x8000, (first[L] + cnt[L]) << (15 - L)), ("limit", L)
+            assert int(base[L]) == (off[L] - first[L]) & 0xffff, ("base", L)
+        want = np.zeros(1 << bits, np.uint16)
+        nxt = list(first)
+        for l, s in order:
+            codeword = nxt[l]
+            nxt[l] += 1
+            if l <= bits:
+                rev = int(format(codeword, "0%db" % l)[::-1], 2)
+                want[rev:: 1 << l] = s | (l << 10)
+            else:
+                rev = int(format(codeword >> (l - bits), "0%db" % bits)[::-1], 2)
+                want[rev] = 0xffff
+        assert np.array_equal(lut, want), ("lut", kind, sorted(code))
