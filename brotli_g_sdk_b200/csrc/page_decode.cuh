@@ -1021,7 +1021,14 @@ BGX_COLD bool slow_round(SlowRound* a) {
     const uint32_t rows = (want + 31u) >> 5;
     const uint32_t c = last_virtual ? s_mine : (s_mine < rows ? s_mine : rows);
     const uint32_t total = __reduce_add_sync(kFull, c);
-    if (have + total < vr_ins || !pc.wait_lit_room(total)) {   // the stream does not carry the literals it inserts
+    if (have + total < vr_ins) {   // the stream does not carry the literals it inserts
+      pc.publish_abort(kPageErrLiterals);
+      return false;
+    }
+    // (Inside a long literal run the literal ring is the bottleneck: a virtual round's literals only fit once the consumer
+    //  has placed the previous round's. Decoding the rows that fit before that wait and the rest after it was measured
+    //  and lost: textures 172 -> 165 GB/s, binary -3 % -- a second inlined literal loop costs more than the overlap buys.)
+    if (!pc.wait_lit_room(total)) {
       pc.publish_abort(kPageErrLiterals);
       return false;
     }
@@ -1338,9 +1345,10 @@ BGX_COLD void cold_flush_bytes(const WarpSmem* sm, uint8_t* out, uint32_t from, 
 // flush are then always aligned). Every round the consumer sees was validated by the producer (it fits the page,
 // every match starts inside the page), so nothing here can fail.
 #ifndef BGX_PIECE_BATCH
-#define BGX_PIECE_BATCH 2
+#define BGX_PIECE_BATCH 1
 #endif
-constexpr int kPieceBatch = BGX_PIECE_BATCH;   // chunks (of 32 pieces) whose source loads are issued back to back
+constexpr int kPieceBatch = BGX_PIECE_BATCH;   // chunks (of 32 pieces) whose source loads are issued back to back (2 was the
+                                               // better depth until the kernel shrank; now 1 wins by 1-2 %, 4 loses 3 %)
 
 BGX_DEV void consumer_warp(const PageJob& job, WarpSmem* sm) {
   const uint32_t lane = pinned(lane_id());
@@ -1427,9 +1435,9 @@ BGX_DEV void consumer_warp(const PageJob& job, WarpSmem* sm) {
     //      (perfectly balanced, any length mix). Ready copies are compacted into tab2[]; a per-chunk bit mask of
     //      their first piece index turns "which copy owns piece t" into one popc. A piece is fetched as two aligned
     //      words + a funnel shift, from the ring (near) or from L2 (far matches: everything below `flushed` is in
-    //      global memory, and ring_lo + 512 < flushed). The source words of up to kPieceBatch chunks are requested
-    //      back to back before the first of them is stored (the pieces of a wave are independent), so that the
-    //      round pays the L2 latency of its far matches once, not once per chunk.
+    //      global memory, and ring_lo + 512 < flushed). The source words of kPieceBatch chunks can be requested
+    //      back to back before the first of them is stored (the pieces of a wave are independent: a round then pays
+    //      the L2 latency of its far matches once per batch, not once per chunk); the depth is 1 today, see kPieceBatch.
     uint32_t pending = __ballot_sync(kFull, cpy != 0);
     if (pending) {
       const uint32_t first = (uint32_t)__ffs((int)pending) - 1u;
