@@ -36,7 +36,7 @@ def last_json_line(path):
 
 
 # ---- bench lines (one JSON object per file, pretty enough to diff)
-for name in ("bench_n1.json", "bench_reference_arm.json", "bench_random.json", "bench_texture.json", "bench_n2.json", "bench_n8.json"):   # (n2 / n8: separate multi-GPU calls)
+for name in ("bench_n1.json", "bench_reference_arm.json", "bench_random.json", "bench_texture.json", "bench_n2.json", "bench_n4.json", "bench_n8.json"):   # (n2 / n8: separate multi-GPU calls)
     if have(name):
         obj = last_json_line(SRC + name)
         if obj:
